@@ -1,0 +1,266 @@
+"""ctypes binding of the C ABI in include/ccz_b200.h (libccz_b200.so, built by build.py).
+
+The library is the only compute path: loading fails loudly when the .so is missing and every
+wrapper raises on a non-zero status.  Tensors own all device memory; wrappers pass raw
+``data_ptr()`` values and the current torch CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import build as _build
+
+BOARD_BYTES = 96
+MAX_MOVES = 128
+N_ACTIONS = 2086
+PLANE_ELEMS = 10710
+KEY_WINDOW = 128
+
+FLAG_CHECK, FLAG_NOMOVES, FLAG_INSUFFICIENT, FLAG_FOURFOLD, FLAG_SIXTY = 1, 2, 4, 8, 16
+FLAG_TIE_MASK = FLAG_INSUFFICIENT | FLAG_FOURFOLD | FLAG_SIXTY
+STATUS_NODE_OVERFLOW = 1
+POLICY_PROBS, POLICY_LOGITS = 0, 1
+
+EXPORTS = (
+    "ccz_version", "ccz_last_error", "ccz_init", "ccz_action_table", "ccz_boards_start",
+    "ccz_movegen_encode", "ccz_board_keys_init", "ccz_board_push", "ccz_mcts_reset", "ccz_mcts_select",
+    "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack",
+)
+
+
+class CczError(RuntimeError):
+    pass
+
+
+class ArenaStruct(ctypes.Structure):
+    """Mirror of ``ccz_arena`` (include/ccz_b200.h)."""
+
+    _fields_ = [
+        ("n_games", ctypes.c_int32),
+        ("node_cap", ctypes.c_int32),
+        ("d_visits", ctypes.c_void_p),
+        ("d_value", ctypes.c_void_p),
+        ("d_prior", ctypes.c_void_p),
+        ("d_move", ctypes.c_void_p),
+        ("d_first_child", ctypes.c_void_p),
+        ("d_n_child", ctypes.c_void_p),
+        ("d_parent", ctypes.c_void_p),
+        ("d_root", ctypes.c_void_p),
+        ("d_n_nodes", ctypes.c_void_p),
+        ("d_status", ctypes.c_void_p),
+        ("d_root_boards", ctypes.c_void_p),
+        ("d_root_keys", ctypes.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.OUT
+
+
+def load() -> ctypes.CDLL:
+    """Load libccz_b200.so (no fallback: a missing library is an error)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise CczError(
+            f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a); there is no CPU fallback"
+        )
+    lib = ctypes.CDLL(path)
+    vp, i32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.ccz_version.restype = i32
+    lib.ccz_last_error.restype = ctypes.c_char_p
+    lib.ccz_init.restype = i32
+    lib.ccz_action_table.argtypes = [vp, vp, vp]
+    lib.ccz_boards_start.argtypes = [vp, i32, vp]
+    lib.ccz_movegen_encode.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.ccz_board_keys_init.argtypes = [vp, i32, vp, vp]
+    lib.ccz_board_push.argtypes = [vp, vp, i32, vp, vp]
+    lib.ccz_mcts_reset.argtypes = [ctypes.POINTER(ArenaStruct), vp]
+    lib.ccz_mcts_select.argtypes = [ctypes.POINTER(ArenaStruct), f32, vp, vp, vp]
+    lib.ccz_mcts_expand_backup.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.ccz_mcts_root_visits.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp, vp, vp]
+    lib.ccz_mcts_advance.argtypes = [ctypes.POINTER(ArenaStruct), ctypes.POINTER(ArenaStruct), vp, vp]
+    lib.ccz_replay_pack.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    for name in EXPORTS:
+        if name not in ("ccz_last_error",):
+            getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ccz_last_error().decode("utf-8", "replace")
+        raise CczError(f"{what} failed ({rc}): {msg}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CczError("device tensor expected (the C ABI takes device pointers)")
+    if not t.is_contiguous():
+        raise CczError("contiguous tensor expected")
+    return t.data_ptr()
+
+
+def host_action_table():
+    """(id_of[90,90] int16, from_of[2086] uint8, to_of[2086] uint8) from the library (host side)."""
+    id_of = np.empty(8100, dtype=np.int16)
+    fr = np.empty(N_ACTIONS, dtype=np.uint8)
+    to = np.empty(N_ACTIONS, dtype=np.uint8)
+    n = load().ccz_action_table(id_of.ctypes.data, fr.ctypes.data, to.ctypes.data)
+    if n != N_ACTIONS:
+        raise CczError(f"ccz_action_table returned {n}")
+    return id_of.reshape(90, 90), fr, to
+
+
+# ---- tensor-level wrappers ------------------------------------------------------------------
+
+def boards_start(n: int, device="cuda") -> torch.Tensor:
+    boards = torch.empty((n, BOARD_BYTES), dtype=torch.uint8, device=device)
+    with torch.cuda.device(boards.device):
+        check(load().ccz_boards_start(_ptr(boards), n, stream_ptr(boards.device)), "ccz_boards_start")
+    return boards
+
+
+def movegen_encode(boards: torch.Tensor, planes: bool = True, out=None):
+    """boards [n,96] uint8 (cuda) -> (move_ids [n,128] i16, counts [n] i16, flags [n] u8, planes [n,17,7,10,9] bf16|None).
+
+    ``out`` may carry preallocated (move_ids, counts, flags, planes) tensors.
+    """
+    n = boards.shape[0]
+    dev = boards.device
+    if out is None:
+        move_ids = torch.empty((n, MAX_MOVES), dtype=torch.int16, device=dev)
+        counts = torch.empty((n,), dtype=torch.int16, device=dev)
+        flags = torch.empty((n,), dtype=torch.uint8, device=dev)
+        pl = torch.empty((n, 17, 7, 10, 9), dtype=torch.bfloat16, device=dev) if planes else None
+    else:
+        move_ids, counts, flags, pl = out
+    with torch.cuda.device(dev):
+        check(
+            load().ccz_movegen_encode(_ptr(boards), n, _ptr(move_ids), _ptr(counts), _ptr(flags), _ptr(pl),
+                                      stream_ptr(dev)),
+            "ccz_movegen_encode",
+        )
+    return move_ids, counts, flags, pl
+
+
+def board_keys_init(boards: torch.Tensor) -> torch.Tensor:
+    n = boards.shape[0]
+    keys = torch.empty((n, KEY_WINDOW), dtype=torch.int64, device=boards.device)
+    with torch.cuda.device(boards.device):
+        check(load().ccz_board_keys_init(_ptr(boards), n, _ptr(keys), stream_ptr(boards.device)),
+              "ccz_board_keys_init")
+    return keys
+
+
+def board_push(boards: torch.Tensor, move_ids: torch.Tensor, keys: torch.Tensor | None = None) -> None:
+    n = boards.shape[0]
+    if move_ids.dtype != torch.int16 or move_ids.numel() != n:
+        raise CczError("move_ids must be int16 [n]")
+    with torch.cuda.device(boards.device):
+        check(load().ccz_board_push(_ptr(boards), _ptr(move_ids), n, _ptr(keys), stream_ptr(boards.device)),
+              "ccz_board_push")
+
+
+class Arena:
+    """Device arrays of one flat MCTS arena (see ``ccz_arena`` in include/ccz_b200.h)."""
+
+    def __init__(self, n_games: int, node_cap: int, device="cuda"):
+        self.n_games, self.node_cap = int(n_games), int(node_cap)
+        self.device = torch.device(device)
+        total = self.n_games * self.node_cap
+        z = dict(device=self.device)
+        self.visits = torch.zeros(total, dtype=torch.int32, **z)
+        self.value = torch.zeros(total, dtype=torch.float32, **z)
+        self.prior = torch.zeros(total, dtype=torch.float32, **z)
+        self.move = torch.zeros(total, dtype=torch.int16, **z)
+        self.first_child = torch.zeros(total, dtype=torch.int32, **z)
+        self.n_child = torch.zeros(total, dtype=torch.int16, **z)
+        self.parent = torch.zeros(total, dtype=torch.int32, **z)
+        self.root = torch.zeros(self.n_games, dtype=torch.int32, **z)
+        self.n_nodes = torch.zeros(self.n_games, dtype=torch.int32, **z)
+        self.status = torch.zeros(self.n_games, dtype=torch.int32, **z)
+        self.root_boards = torch.zeros((self.n_games, BOARD_BYTES), dtype=torch.uint8, **z)
+        self.root_keys = torch.zeros((self.n_games, KEY_WINDOW), dtype=torch.int64, **z)
+        self.struct = ArenaStruct(
+            self.n_games, self.node_cap, self.visits.data_ptr(), self.value.data_ptr(), self.prior.data_ptr(),
+            self.move.data_ptr(), self.first_child.data_ptr(), self.n_child.data_ptr(), self.parent.data_ptr(),
+            self.root.data_ptr(), self.n_nodes.data_ptr(), self.status.data_ptr(), self.root_boards.data_ptr(),
+            self.root_keys.data_ptr(),
+        )
+
+    @property
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+    def bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (
+            self.visits, self.value, self.prior, self.move, self.first_child, self.n_child, self.parent,
+            self.root, self.n_nodes, self.status, self.root_boards, self.root_keys))
+
+
+def mcts_reset(a: Arena) -> None:
+    with torch.cuda.device(a.device):
+        check(load().ccz_mcts_reset(a.ref, stream_ptr(a.device)), "ccz_mcts_reset")
+
+
+def mcts_select(a: Arena, c_puct: float, leaf_boards: torch.Tensor, leaf_nodes: torch.Tensor) -> None:
+    with torch.cuda.device(a.device):
+        check(load().ccz_mcts_select(a.ref, float(c_puct), _ptr(leaf_boards), _ptr(leaf_nodes), stream_ptr(a.device)),
+              "ccz_mcts_select")
+
+
+def mcts_expand_backup(a: Arena, leaf_nodes, policy, policy_kind, values, move_ids, counts, flags) -> None:
+    if policy.dtype != torch.float32 or values.dtype != torch.float32:
+        raise CczError("policy and values must be float32")
+    with torch.cuda.device(a.device):
+        check(
+            load().ccz_mcts_expand_backup(a.ref, _ptr(leaf_nodes), _ptr(policy), int(policy_kind), _ptr(values),
+                                          _ptr(move_ids), _ptr(counts), _ptr(flags), stream_ptr(a.device)),
+            "ccz_mcts_expand_backup",
+        )
+
+
+def mcts_root_visits(a: Arena, acts, visits, counts) -> None:
+    with torch.cuda.device(a.device):
+        check(load().ccz_mcts_root_visits(a.ref, _ptr(acts), _ptr(visits), _ptr(counts), stream_ptr(a.device)),
+              "ccz_mcts_root_visits")
+
+
+def mcts_advance(src: Arena, dst: Arena, chosen: torch.Tensor) -> None:
+    if chosen.dtype != torch.int16:
+        raise CczError("chosen must be int16")
+    with torch.cuda.device(src.device):
+        check(load().ccz_mcts_advance(src.ref, dst.ref, _ptr(chosen), stream_ptr(src.device)), "ccz_mcts_advance")
+
+
+def replay_pack(hist_boards, turn_plane, acts, probs, counts):
+    """-> (states [2n,17,7,10,9] f16, pi [2n,2086] f64) on the device."""
+    n = hist_boards.shape[0]
+    dev = hist_boards.device
+    states = torch.empty((2 * n, 17, 7, 10, 9), dtype=torch.float16, device=dev)
+    pi = torch.empty((2 * n, N_ACTIONS), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(
+            load().ccz_replay_pack(_ptr(hist_boards), _ptr(turn_plane), _ptr(acts), _ptr(probs), _ptr(counts), n,
+                                   _ptr(states), _ptr(pi), stream_ptr(dev)),
+            "ccz_replay_pack",
+        )
+    return states, pi

@@ -1,0 +1,296 @@
+// ccz_b200.cu -- C-ABI entry points (include/ccz_b200.h) over the sm_100a kernels.
+// One translation unit: the constant tables in ccz_rules.cuh are shared by all kernels.
+#include "../../include/ccz_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "ccz_movegen.cuh"
+#include "ccz_mcts.cuh"
+#include "ccz_replay.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) {
+        g_err += ": ";
+        g_err += cudaGetErrorString(e);
+    }
+    return code;
+}
+
+#define CCZ_CUDA(call)                                      \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return fail(-2, #call, e_);  \
+    } while (0)
+
+// ---- host-side constant tables -------------------------------------------------------------
+struct HostTables {
+    int16_t id_of[8100];
+    uint8_t from_of[ccz::N_ACTIONS], to_of[ccz::N_ACTIONS];
+    int16_t flip_of[ccz::N_ACTIONS];
+    uint64_t zkeys[16 * 90 + 1];
+    uint8_t start[ccz::BOARD_BYTES];
+    bool built = false;
+};
+HostTables g_tab;
+bool g_dev_ready[64] = {false};
+
+int sq_of(const char *s) { return (s[0] - 'a') + 9 * (s[1] - '0'); }
+
+// The fixed 2086-entry action table (tools.py:172-272): per source square in rank-major order
+// the 9 same-file destinations by rank, the 8 same-rank destinations by file, then the knight
+// jumps (drank,dfile) = (-2,-1) (-1,-2) (-2,1) (1,-2) (2,-1) (-1,2) (2,1) (1,2) that stay on
+// the board; then the 16 advisor and 32 elephant moves in the reference's literal order.
+void build_tables() {
+    if (g_tab.built) return;
+    HostTables &t = g_tab;
+    for (int i = 0; i < 8100; ++i) t.id_of[i] = -1;
+    int idx = 0;
+    auto add = [&](int from, int to) {
+        t.id_of[from * 90 + to] = (int16_t)idx;
+        t.from_of[idx] = (uint8_t)from;
+        t.to_of[idx] = (uint8_t)to;
+        ++idx;
+    };
+    static const int kn[8][2] = {{-2, -1}, {-1, -2}, {-2, 1}, {1, -2}, {2, -1}, {-1, 2}, {2, 1}, {1, 2}};
+    for (int rank = 0; rank < 10; ++rank)
+        for (int file = 0; file < 9; ++file) {
+            const int from = file + 9 * rank;
+            for (int r2 = 0; r2 < 10; ++r2)
+                if (r2 != rank) add(from, file + 9 * r2);
+            for (int f2 = 0; f2 < 9; ++f2)
+                if (f2 != file) add(from, f2 + 9 * rank);
+            for (auto &k : kn) {
+                const int r2 = rank + k[0], f2 = file + k[1];
+                if (r2 >= 0 && r2 < 10 && f2 >= 0 && f2 < 9) add(from, f2 + 9 * r2);
+            }
+        }
+    static const char *const advisor[] = {"d0e1", "e1d0", "f0e1", "e1f0", "d2e1", "e1d2", "f2e1", "e1f2",
+                                          "d9e8", "e8d9", "f9e8", "e8f9", "d7e8", "e8d7", "f7e8", "e8f7"};
+    static const char *const elephant[] = {
+        "a2c0", "c0a2", "a2c4", "c4a2", "c0e2", "e2c0", "c4e2", "e2c4", "e2g0", "g0e2", "e2g4",
+        "g4e2", "g0i2", "i2g0", "g4i2", "i2g4", "a7c5", "c5a7", "a7c9", "c9a7", "c5e7", "e7c5",
+        "c9e7", "e7c9", "e7g5", "g5e7", "e7g9", "g9e7", "g5i7", "i7g5", "g9i7", "i7g9"};
+    for (const char *m : advisor) add(sq_of(m), sq_of(m + 2));
+    for (const char *m : elephant) add(sq_of(m), sq_of(m + 2));
+    // file mirror of every action (tools.py:133-164, collect.py:117-122)
+    for (int i = 0; i < ccz::N_ACTIONS; ++i) {
+        const int f = t.from_of[i], to = t.to_of[i];
+        const int mf = (8 - f % 9) + 9 * (f / 9), mt = (8 - to % 9) + 9 * (to / 9);
+        t.flip_of[i] = t.id_of[mf * 90 + mt];
+    }
+    // position keys: splitmix64 stream
+    uint64_t x = 0x0123456789ABCDEFull;
+    for (int i = 0; i < 16 * 90 + 1; ++i) {
+        x += 0x9E3779B97F4A7C15ull;
+        uint64_t z = x;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        t.zkeys[i] = z ^ (z >> 31);
+    }
+    // start position: rnbakabnr/9/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RNBAKABNR w
+    std::memset(t.start, 0, sizeof(t.start));
+    static const uint8_t back[9] = {3, 4, 5, 6, 7, 6, 5, 4, 3};
+    for (int f = 0; f < 9; ++f) {
+        t.start[f] = back[f];
+        t.start[81 + f] = back[f] | 8;
+    }
+    t.start[19] = t.start[25] = 2;
+    t.start[64] = t.start[70] = 2 | 8;
+    for (int f = 0; f < 9; f += 2) {
+        t.start[27 + f] = 1;
+        t.start[54 + f] = 1 | 8;
+    }
+    t.start[ccz::OFF_TURN] = 1;
+    t.built = (idx == ccz::N_ACTIONS);
+}
+
+int ensure_device() {
+    build_tables();
+    if (!g_tab.built) return fail(-3, "action table construction failed");
+    int dev = 0;
+    CCZ_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(-3, "device index out of range");
+    if (g_dev_ready[dev]) return 0;
+    CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_id_of, g_tab.id_of, sizeof(g_tab.id_of)));
+    CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_from_of, g_tab.from_of, sizeof(g_tab.from_of)));
+    CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_to_of, g_tab.to_of, sizeof(g_tab.to_of)));
+    CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_flip_of, g_tab.flip_of, sizeof(g_tab.flip_of)));
+    CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_zkeys, g_tab.zkeys, sizeof(g_tab.zkeys)));
+    CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_start_board, g_tab.start, sizeof(g_tab.start)));
+    g_dev_ready[dev] = true;
+    return 0;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(-2, what, e);
+    return 0;
+}
+
+int check_arena(const ccz_arena *a) {
+    if (!a) return fail(-1, "arena is NULL");
+    if (a->n_games <= 0 || a->node_cap <= 1) return fail(-1, "arena geometry invalid");
+    if (!a->d_visits || !a->d_value || !a->d_prior || !a->d_move || !a->d_first_child || !a->d_n_child ||
+        !a->d_parent || !a->d_root || !a->d_n_nodes || !a->d_status || !a->d_root_boards || !a->d_root_keys)
+        return fail(-1, "arena has a NULL array");
+    return 0;
+}
+
+inline int warps_grid(int n) { return (n + ccz::MCTS_WARPS - 1) / ccz::MCTS_WARPS; }
+
+} // namespace
+
+extern "C" {
+
+int ccz_version(void) { return 100; }
+
+const char *ccz_last_error(void) { return g_err.c_str(); }
+
+int ccz_init(void) { return ensure_device(); }
+
+int ccz_action_table(int16_t *id_of, uint8_t *from_of, uint8_t *to_of) {
+    build_tables();
+    if (!g_tab.built) return fail(-3, "action table construction failed");
+    if (id_of) std::memcpy(id_of, g_tab.id_of, sizeof(g_tab.id_of));
+    if (from_of) std::memcpy(from_of, g_tab.from_of, sizeof(g_tab.from_of));
+    if (to_of) std::memcpy(to_of, g_tab.to_of, sizeof(g_tab.to_of));
+    return ccz::N_ACTIONS;
+}
+
+int ccz_boards_start(uint8_t *d_boards, int n, ccz_stream_t s) {
+    if (n < 0 || (n > 0 && !d_boards)) return fail(-1, "ccz_boards_start: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    if (n == 0) return 0;
+    const int threads = 256, total = n * 6;
+    ccz::boards_start_kernel<<<(total + threads - 1) / threads, threads, 0, s>>>(d_boards, n);
+    return check_launch("boards_start_kernel");
+}
+
+int ccz_movegen_encode(const uint8_t *d_boards, int n, int16_t *d_move_ids, int16_t *d_counts, uint8_t *d_flags,
+                       void *d_planes_bf16, ccz_stream_t s) {
+    if (n < 0) return fail(-1, "ccz_movegen_encode: n < 0");
+    if (n == 0) return 0;
+    if (!d_boards || !d_move_ids || !d_counts || !d_flags) return fail(-1, "ccz_movegen_encode: NULL pointer");
+    if (((uintptr_t)d_boards & 15) || ((uintptr_t)d_move_ids & 7) || ((uintptr_t)d_planes_bf16 & 15))
+        return fail(-1, "ccz_movegen_encode: boards/planes must be 16-byte, move_ids 8-byte aligned");
+    if (int rc = ensure_device()) return rc;
+    const int n_quads = (n + 3) / 4;
+    int grid = (n_quads + ccz::MG_WARPS - 1) / ccz::MG_WARPS;
+    const int cap = sm_count() * 8;
+    if (grid > cap) grid = cap;
+    ccz::movegen_encode_kernel<<<grid, ccz::MG_WARPS * 32, 0, s>>>(d_boards, n, d_move_ids, d_counts, d_flags,
+                                                                  static_cast<uint32_t *>(d_planes_bf16));
+    return check_launch("movegen_encode_kernel");
+}
+
+int ccz_board_keys_init(const uint8_t *d_boards, int n, uint64_t *d_keys, ccz_stream_t s) {
+    if (n < 0 || (n > 0 && (!d_boards || !d_keys))) return fail(-1, "ccz_board_keys_init: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    if (n == 0) return 0;
+    CCZ_CUDA(cudaMemsetAsync(d_keys, 0xFF, (size_t)n * ccz::KEY_WINDOW * sizeof(uint64_t), s));
+    ccz::board_keys_init_kernel<<<warps_grid(n), ccz::MCTS_WARPS * 32, 0, s>>>(d_boards, n, d_keys);
+    return check_launch("board_keys_init_kernel");
+}
+
+int ccz_board_push(uint8_t *d_boards, const int16_t *d_move_ids, int n, uint64_t *d_keys, ccz_stream_t s) {
+    if (n < 0 || (n > 0 && (!d_boards || !d_move_ids))) return fail(-1, "ccz_board_push: bad arguments");
+    if (int rc = ensure_device()) return rc;
+    if (n == 0) return 0;
+    ccz::board_push_kernel<<<warps_grid(n), ccz::MCTS_WARPS * 32, 0, s>>>(d_boards, d_move_ids, n, d_keys);
+    return check_launch("board_push_kernel");
+}
+
+int ccz_mcts_reset(const ccz_arena *a, ccz_stream_t s) {
+    if (int rc = check_arena(a)) return rc;
+    if (int rc = ensure_device()) return rc;
+    ccz::mcts_reset_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a);
+    return check_launch("mcts_reset_kernel");
+}
+
+int ccz_mcts_select(const ccz_arena *a, float c_puct, uint8_t *d_leaf_boards, int32_t *d_leaf_nodes,
+                    ccz_stream_t s) {
+    if (int rc = check_arena(a)) return rc;
+    if (!d_leaf_boards || !d_leaf_nodes) return fail(-1, "ccz_mcts_select: NULL output");
+    if (int rc = ensure_device()) return rc;
+    ccz::mcts_select_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, c_puct, d_leaf_boards,
+                                                                                   d_leaf_nodes);
+    return check_launch("mcts_select_kernel");
+}
+
+int ccz_mcts_expand_backup(const ccz_arena *a, const int32_t *d_leaf_nodes, const float *d_policy, int policy_kind,
+                           const float *d_values, const int16_t *d_move_ids, const int16_t *d_counts,
+                           const uint8_t *d_flags, ccz_stream_t s) {
+    if (int rc = check_arena(a)) return rc;
+    if (!d_leaf_nodes || !d_policy || !d_values || !d_move_ids || !d_counts || !d_flags)
+        return fail(-1, "ccz_mcts_expand_backup: NULL pointer");
+    if (policy_kind != CCZ_POLICY_PROBS && policy_kind != CCZ_POLICY_LOGITS)
+        return fail(-1, "ccz_mcts_expand_backup: unknown policy_kind");
+    if (int rc = ensure_device()) return rc;
+    ccz::mcts_expand_backup_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(
+        *a, d_leaf_nodes, d_policy, policy_kind, d_values, d_move_ids, d_counts, d_flags);
+    return check_launch("mcts_expand_backup_kernel");
+}
+
+int ccz_mcts_root_visits(const ccz_arena *a, int16_t *d_acts, int32_t *d_visits, int16_t *d_counts,
+                         ccz_stream_t s) {
+    if (int rc = check_arena(a)) return rc;
+    if (!d_acts || !d_visits || !d_counts) return fail(-1, "ccz_mcts_root_visits: NULL output");
+    if (int rc = ensure_device()) return rc;
+    ccz::mcts_root_visits_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, d_acts, d_visits,
+                                                                                        d_counts);
+    return check_launch("mcts_root_visits_kernel");
+}
+
+int ccz_mcts_advance(const ccz_arena *src, const ccz_arena *dst, const int16_t *d_chosen, ccz_stream_t s) {
+    if (int rc = check_arena(src)) return rc;
+    if (int rc = check_arena(dst)) return rc;
+    if (!d_chosen) return fail(-1, "ccz_mcts_advance: NULL chosen");
+    if (src->n_games != dst->n_games || src->node_cap != dst->node_cap)
+        return fail(-1, "ccz_mcts_advance: src/dst geometry differs");
+    if (src->d_visits == dst->d_visits) return fail(-1, "ccz_mcts_advance: src and dst must be distinct");
+    if (int rc = ensure_device()) return rc;
+    ccz::mcts_advance_kernel<<<warps_grid(src->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*src, *dst, d_chosen);
+    return check_launch("mcts_advance_kernel");
+}
+
+int ccz_replay_pack(const uint8_t *d_hist_boards, const uint8_t *d_turn_plane, const int16_t *d_acts,
+                    const double *d_probs, const int16_t *d_counts, int n, void *d_states_f16, double *d_pi,
+                    ccz_stream_t s) {
+    if (n < 0) return fail(-1, "ccz_replay_pack: n < 0");
+    if (n == 0) return 0;
+    if (!d_hist_boards || !d_turn_plane || !d_acts || !d_probs || !d_counts || !d_states_f16 || !d_pi)
+        return fail(-1, "ccz_replay_pack: NULL pointer");
+    if (int rc = ensure_device()) return rc;
+    const long long words = 2ll * n * ccz::WORDS_PER_POS;
+    const int threads = 256;
+    const long long blocks = (words + threads - 1) / threads;
+    if (blocks > 0x7fffffffll) return fail(-1, "ccz_replay_pack: n too large");
+    ccz::replay_states_kernel<<<(unsigned)blocks, threads, 0, s>>>(d_hist_boards, d_turn_plane, n,
+                                                                   static_cast<uint32_t *>(d_states_f16));
+    if (int rc = check_launch("replay_states_kernel")) return rc;
+    CCZ_CUDA(cudaMemsetAsync(d_pi, 0, (size_t)2 * n * ccz::N_ACTIONS * sizeof(double), s));
+    ccz::replay_pi_kernel<<<(n * 32 + threads - 1) / threads, threads, 0, s>>>(d_acts, d_probs, d_counts, n, d_pi);
+    return check_launch("replay_pi_kernel");
+}
+
+} // extern "C"

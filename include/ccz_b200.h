@@ -1,0 +1,149 @@
+/*
+ * ccz_b200.h -- C ABI of the B200-native Xiangqi self-play hot path.
+ *
+ * This is the drop-in boundary.  The reference (Symb0x76/ChineseChessZero) is
+ * pure Python and has no FFI; its seams are Python call signatures.  Each entry point below
+ * replaces the arithmetic behind one of those seams and is what a ctypes binding in the
+ * reference's own files would call (INTEGRATION.md shows the stubs):
+ *
+ *   ccz_movegen_encode      <- board.legal_moves + move_action2move_id (net.py:154-157),
+ *                              decode_board + plane assembly (tools.py:74-106, net.py:160-177),
+ *                              is_game_over / is_tie predicates (tools.py:109-123, mcts.py:116)
+ *   ccz_board_push          <- board.push (game.py:201, mcts.py:111)
+ *   ccz_mcts_select         <- Node.select / puct_value + path pushes (mcts.py:41-61,105-111)
+ *   ccz_mcts_expand_backup  <- exp(log_p)[legal] gather (net.py:202-203), Node.expand
+ *                              (mcts.py:31-39), terminal values (mcts.py:116-126),
+ *                              update_recursive (mcts.py:63-78)
+ *   ccz_mcts_root_visits    <- root child visit read-out (mcts.py:163-164)
+ *   ccz_mcts_advance        <- MCTS.update_with_move (mcts.py:168-178) + board.push of the move
+ *   ccz_replay_pack         <- CollectPipeline.preprocess / flip_data (collect.py:64-131)
+ *
+ * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller (torch tensors
+ * on the Python side); the library never allocates device memory, never synchronises, and
+ * enqueues all work on the given stream.  Return value 0 = OK, negative = error, message via
+ * ccz_last_error().  Thread-compatible: one host thread per device at a time.
+ */
+#ifndef CCZ_B200_H
+#define CCZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *ccz_stream_t; /* == cudaStream_t */
+
+#define CCZ_BOARD_BYTES 96   /* sq[90], turn, halfmove clock, repetition count, 3 pad */
+#define CCZ_MAX_MOVES 128    /* >= max legal moves of any Xiangqi position (119) */
+#define CCZ_N_ACTIONS 2086   /* tools.py:172-272 */
+#define CCZ_PLANE_ELEMS 10710 /* 17*7*10*9, net.py:12-13 */
+#define CCZ_KEY_WINDOW 128   /* position keys kept since the last capture */
+
+/* flag byte written by ccz_movegen_encode */
+#define CCZ_FLAG_CHECK 1        /* side to move is in check */
+#define CCZ_FLAG_NOMOVES 2      /* no legal move: checkmate (with CHECK) or stalemate */
+#define CCZ_FLAG_INSUFFICIENT 4 /* board.is_insufficient_material() */
+#define CCZ_FLAG_FOURFOLD 8     /* board.is_fourfold_repetition() */
+#define CCZ_FLAG_SIXTY 16       /* board.is_sixty_moves() */
+#define CCZ_FLAG_TIE_MASK (CCZ_FLAG_INSUFFICIENT | CCZ_FLAG_FOURFOLD | CCZ_FLAG_SIXTY)
+
+/* per-game status bits (ccz_arena.d_status) */
+#define CCZ_STATUS_NODE_OVERFLOW 1
+
+/* kinds of policy input accepted by ccz_mcts_expand_backup */
+#define CCZ_POLICY_PROBS 0  /* fp32 probabilities, gathered as-is (bit-exact path) */
+#define CCZ_POLICY_LOGITS 1 /* fp32 logits; softmax over all 2086 fused into the gather */
+
+/* Flat MCTS arena: `n_games` independent trees, each owning `node_cap` node slots.  Node i of
+ * game g lives at index g*node_cap + i of every d_node_* array; the children of a node are the
+ * contiguous slots [first_child, first_child + n_child) in cchess generation order (the
+ * reference's insertion-ordered dict, mcts.py:37-39). */
+typedef struct {
+    int32_t n_games;
+    int32_t node_cap;
+    int32_t *d_visits;      /* N   (mcts.py:16) */
+    float *d_value;         /* Q   (mcts.py:15), fp32 incremental mean */
+    float *d_prior;         /* P   (mcts.py:17) */
+    int16_t *d_move;        /* action id that leads to this node */
+    int32_t *d_first_child; /* local index of the first child, -1 if none */
+    int16_t *d_n_child;     /* 0 = leaf (mcts.py:19-23) */
+    int32_t *d_parent;      /* local index, -1 for the root */
+    int32_t *d_root;        /* [n_games] local index of the root node */
+    int32_t *d_n_nodes;     /* [n_games] bump pointer */
+    int32_t *d_status;      /* [n_games] CCZ_STATUS_* bits, sticky */
+    uint8_t *d_root_boards; /* [n_games, 96] position at the root */
+    uint64_t *d_root_keys;  /* [n_games, 128] position keys since the last capture; entry
+                               `clock` is the root position itself */
+} ccz_arena;
+
+int ccz_version(void);
+const char *ccz_last_error(void);
+
+/* Upload the constant tables (action table, position-key table) to the current device.  Called
+ * implicitly by every entry point; exposed so start-up cost can be kept out of timed regions. */
+int ccz_init(void);
+
+/* Host copies of the action table: id_of[from*90+to] (-1 = not an action), from/to square of
+ * each id.  Any pointer may be NULL. */
+int ccz_action_table(int16_t *id_of, uint8_t *from_of, uint8_t *to_of);
+
+/* Fill `n` board records with the start position (device memory). */
+int ccz_boards_start(uint8_t *d_boards, int n, ccz_stream_t s);
+
+/* Legal moves (ordered, as action ids, -1 padded), count, flag byte and -- unless d_planes is
+ * NULL -- the dense bf16 (17,7,10,9) search-time net input for each of n board records. */
+int ccz_movegen_encode(const uint8_t *d_boards, int n, int16_t *d_move_ids /*[n,128]*/,
+                       int16_t *d_counts /*[n]*/, uint8_t *d_flags /*[n]*/,
+                       void *d_planes_bf16 /*[n,10710] or NULL*/, ccz_stream_t s);
+
+/* Apply move id d_move_ids[i] to board record i (ids < 0 leave the board untouched).  If
+ * d_keys is not NULL it is the [n,128] key window of each board and is updated so that the
+ * record's repetition count stays exact. */
+int ccz_board_push(uint8_t *d_boards, const int16_t *d_move_ids, int n, uint64_t *d_keys,
+                   ccz_stream_t s);
+
+/* Initialise the [n,128] key windows of history-less board records (entry `clock` = the key of
+ * the record, earlier entries = a sentinel that matches nothing). */
+int ccz_board_keys_init(const uint8_t *d_boards, int n, uint64_t *d_keys, ccz_stream_t s);
+
+/* Reset every tree to a single unvisited root (Node(None, 1.0), mcts.py:94) over the start
+ * position. */
+int ccz_mcts_reset(const ccz_arena *a, ccz_stream_t s);
+
+/* One selection pass per game: descend by PUCT from the root to a leaf, replaying the moves.
+ * Writes the leaf position and the leaf's local node index. */
+int ccz_mcts_select(const ccz_arena *a, float c_puct, uint8_t *d_leaf_boards /*[n,96]*/,
+                    int32_t *d_leaf_nodes /*[n]*/, ccz_stream_t s);
+
+/* Expand each leaf (unless terminal) with priors gathered from d_policy[n,2086] and back the
+ * leaf value up to the root with alternating sign. */
+int ccz_mcts_expand_backup(const ccz_arena *a, const int32_t *d_leaf_nodes, const float *d_policy,
+                           int policy_kind, const float *d_values /*[n]*/,
+                           const int16_t *d_move_ids, const int16_t *d_counts,
+                           const uint8_t *d_flags, ccz_stream_t s);
+
+/* Root children in generation order: action ids (-1 padded), visit counts, count. */
+int ccz_mcts_root_visits(const ccz_arena *a, int16_t *d_acts /*[n,128]*/,
+                         int32_t *d_visits /*[n,128]*/, int16_t *d_counts /*[n]*/, ccz_stream_t s);
+
+/* Play d_chosen[g] in game g: the chosen child's sub-tree is compacted into `dst` (tree reuse),
+ * the root board and key window advance.  d_chosen[g] == -1 resets game g to the start position
+ * with a fresh root; -2 keeps the position but drops the tree.  src and dst must be distinct
+ * arenas with the same geometry. */
+int ccz_mcts_advance(const ccz_arena *src, const ccz_arena *dst, const int16_t *d_chosen,
+                     ccz_stream_t s);
+
+/* Replay densification (collect.py:64-131): for each of n samples scatter the sparse visit
+ * distribution into a dense float64 row of 2086 and its file-mirrored twin, and write the
+ * (17,7,10,9) float16 state stack and its mirror from 8 board records of history (red planes
+ * of slot i -> play i, black planes of slot i -> play 8+i, game.py:23-44). */
+int ccz_replay_pack(const uint8_t *d_hist_boards /*[n,8,96]: history slots, most recent first*/,
+                    const uint8_t *d_turn_plane /*[n] 1 = ones */, const int16_t *d_acts /*[n,128]*/,
+                    const double *d_probs /*[n,128]*/, const int16_t *d_counts, int n,
+                    void *d_states_f16 /*[2n,10710]*/, double *d_pi /*[2n,2086]*/, ccz_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCZ_B200_H */

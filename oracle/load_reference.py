@@ -1,0 +1,66 @@
+"""load_reference -- CPU ORACLE helper (TEST INFRASTRUCTURE ONLY).
+
+Imports the UNMODIFIED reference modules (tools, mcts, net, game, collect) from /root/reference
+after installing stand-ins for the packages it needs but the container lacks:
+``cchess`` -> oracle.cchess_shim, ``cchess.svg``, ``IPython.display``, ``h5py``, ``frontend``.
+
+/root/reference only exists in the authoring container: tests that use this module skip on the
+GPU box and rely on the golden fixtures under tests/golden/ that scripts/make_golden.py wrote
+from it.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_DIR = os.environ.get("CCZ_REFERENCE_DIR", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_DIR, "mcts.py"))
+
+
+def install_stubs() -> None:
+    from . import cchess_shim
+
+    if "cchess" not in sys.modules or sys.modules["cchess"] is not cchess_shim:
+        sys.modules["cchess"] = cchess_shim
+    svg = types.ModuleType("cchess.svg")
+    svg.board = lambda *a, **k: "<svg/>"
+    sys.modules["cchess.svg"] = svg
+    cchess_shim.svg = svg
+    if "IPython" not in sys.modules:
+        ip = types.ModuleType("IPython")
+        disp = types.ModuleType("IPython.display")
+        disp.display = lambda *a, **k: None
+        disp.SVG = lambda x: x
+        ip.display = disp
+        sys.modules["IPython"] = ip
+        sys.modules["IPython.display"] = disp
+    if "h5py" not in sys.modules:
+        try:
+            importlib.import_module("h5py")
+        except Exception:
+            sys.modules["h5py"] = types.ModuleType("h5py")
+
+
+def load(*names: str):
+    """Return the named unmodified reference modules, e.g. ``tools, mcts = load("tools", "mcts")``."""
+    if not available():
+        raise FileNotFoundError(f"reference not present at {REFERENCE_DIR}")
+    install_stubs()
+    if REFERENCE_DIR not in sys.path:
+        sys.path.append(REFERENCE_DIR)
+    cwd = os.getcwd()
+    mods = []
+    for n in names:
+        key = f"_ccz_ref_{n}"
+        if key in sys.modules:
+            mods.append(sys.modules[key])
+            continue
+        # the reference modules import each other by bare name (tools, parameters, ...)
+        mods.append(importlib.import_module(n))
+    os.chdir(cwd)
+    return mods[0] if len(mods) == 1 else tuple(mods)
