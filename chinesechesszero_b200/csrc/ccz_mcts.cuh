@@ -151,8 +151,10 @@ mcts_expand_backup_kernel(ccz_arena a, const int32_t *leaf_nodes, const float *p
         } else {
             for (int i = lane; i < cnt; i += 32) {
                 const int id = move_ids[(size_t)g * MAX_MOVES + i];
-                float p = pol[id];
-                if (policy_kind == CCZ_POLICY_LOGITS) p = expf(p - mx) * inv;
+                // ids are always valid for reachable positions; a piece on an impossible square
+                // (hand-made records) has no action id and gets prior 0 instead of an OOB read
+                float p = (id >= 0 && id < N_ACTIONS) ? pol[id] : 0.f;
+                if (policy_kind == CCZ_POLICY_LOGITS && id >= 0) p = expf(p - mx) * inv;
                 const size_t c = nb + first + i;
                 a.d_visits[c] = 0;
                 a.d_value[c] = 0.f;

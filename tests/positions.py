@@ -75,7 +75,7 @@ EDGE_CASES = [
     ("pawn_fwd_block", "4k4/4P4/9/9/9/9/9/9/9/4K4 b", 0, 0),
     ("pawn_side_check2", "3Pk4/9/9/9/9/9/9/9/9/5K3 b", 0, 0),
     # elephants: eye blocking and river
-    ("elephant_eye", "4k4/9/9/9/2b6/9/2B6/3P5/9/3K5 w", 0, 0),
+    ("elephant_eye", "4k4/9/9/9/2b6/2B6/3P5/9/9/3K5 w", 0, 0),
     # sixty-move and fourfold flags
     ("sixty", "rnbakabnr/9/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RNBAKABNR w", 120, 0),
     ("sixty_minus_one", "rnbakabnr/9/1c5c1/p1p1p1p1p/9/9/P1P1P1P1P/1C5C1/9/RNBAKABNR b", 119, 2),
