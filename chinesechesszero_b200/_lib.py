@@ -85,7 +85,7 @@ def load() -> ctypes.CDLL:
     lib.ccz_movegen_encode.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.ccz_board_keys_init.argtypes = [vp, i32, vp, vp]
     lib.ccz_board_push.argtypes = [vp, vp, i32, vp, vp]
-    lib.ccz_mcts_reset.argtypes = [ctypes.POINTER(ArenaStruct), vp]
+    lib.ccz_mcts_reset.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp]
     lib.ccz_mcts_select.argtypes = [ctypes.POINTER(ArenaStruct), f32, vp, vp, vp]
     lib.ccz_mcts_expand_backup.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp, i32, vp, vp, vp, vp, vp]
     lib.ccz_mcts_root_visits.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp, vp, vp]
@@ -216,9 +216,11 @@ class Arena:
             self.root, self.n_nodes, self.status, self.root_boards, self.root_keys))
 
 
-def mcts_reset(a: Arena) -> None:
+def mcts_reset(a: Arena, mask: torch.Tensor | None = None) -> None:
+    if mask is not None and (mask.dtype != torch.uint8 or mask.numel() != a.n_games):
+        raise CczError("mask must be uint8 [n_games]")
     with torch.cuda.device(a.device):
-        check(load().ccz_mcts_reset(a.ref, stream_ptr(a.device)), "ccz_mcts_reset")
+        check(load().ccz_mcts_reset(a.ref, _ptr(mask), stream_ptr(a.device)), "ccz_mcts_reset")
 
 
 def mcts_select(a: Arena, c_puct: float, leaf_boards: torch.Tensor, leaf_nodes: torch.Tensor) -> None:

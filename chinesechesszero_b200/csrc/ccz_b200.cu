@@ -220,10 +220,10 @@ int ccz_board_push(uint8_t *d_boards, const int16_t *d_move_ids, int n, uint64_t
     return check_launch("board_push_kernel");
 }
 
-int ccz_mcts_reset(const ccz_arena *a, ccz_stream_t s) {
+int ccz_mcts_reset(const ccz_arena *a, const uint8_t *d_mask, ccz_stream_t s) {
     if (int rc = check_arena(a)) return rc;
     if (int rc = ensure_device()) return rc;
-    ccz::mcts_reset_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a);
+    ccz::mcts_reset_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, d_mask);
     return check_launch("mcts_reset_kernel");
 }
 

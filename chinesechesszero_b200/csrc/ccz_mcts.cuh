@@ -350,11 +350,12 @@ mcts_advance_kernel(ccz_arena src, ccz_arena dst, const int16_t *chosen) {
 }
 
 // Node(None, 1.0) over the start position for every game (mcts.py:94; game.py:148)
-__global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_reset_kernel(ccz_arena a) {
+__global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_reset_kernel(ccz_arena a, const uint8_t *mask) {
     __shared__ __align__(16) uint8_t s_board[MCTS_WARPS][BOARD_BYTES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x * MCTS_WARPS + warp;
     if (g >= a.n_games) return;
+    if (mask != nullptr && mask[g] == 0) return;
     uint8_t *B = s_board[warp];
     if (lane < 6) {
         const uint4 v = reinterpret_cast<const uint4 *>(d_start_board)[lane];

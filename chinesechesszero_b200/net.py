@@ -1,0 +1,208 @@
+"""Host-side mirror of the reference's ``net.py`` for the self-play path.
+
+``Net`` / ``ResBlock`` keep the reference architecture and ``state_dict`` keys (net.py:15-110) so
+reference checkpoints (``torch.save(state_dict)``, net.py:208-209) load unchanged.  The new part
+is :class:`BatchedEvaluator`: the search-time forward evaluated ONCE per lockstep step on the
+whole leaf batch in bf16 through PyTorch (the only dense contraction of the path, hence the only
+tensor-core user): eval-mode BatchNorm folded into the convolutions, channels_last, bias + skip
++ ReLU in cuDNN's fused epilogue, optional CUDA-graph capture.  Policy logits and the value come
+back in fp32; the softmax over all 2086 actions is fused into the expand kernel's gather
+(net.py:202-203 semantics: softmax then gather, no renormalisation).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+
+PIECES = 7  # net.py:12
+PLAYS = 17  # net.py:13
+N_ACTIONS = _lib.N_ACTIONS
+# conv + linear multiply-accumulates of one forward, x2: 8.5506 GFLOP / position
+FLOP_PER_POSITION = 2 * 4_275_314_716
+
+
+class ResBlock(nn.Module):
+    """net.py:15-41 (same attribute names => same state_dict keys)."""
+
+    def __init__(self, num_channels=256):
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_channels, num_channels, kernel_size=(3, 3), stride=(1, 1), padding=1)
+        self.conv1_bn = nn.BatchNorm2d(num_channels)
+        self.conv1_act = nn.ReLU()
+        self.conv2 = nn.Conv2d(num_channels, num_channels, kernel_size=(3, 3), stride=(1, 1), padding=1)
+        self.conv2_bn = nn.BatchNorm2d(num_channels)
+        self.conv2_act = nn.ReLU()
+
+    def forward(self, x):
+        y = self.conv1_act(self.conv1_bn(self.conv1(x)))
+        y = self.conv2_bn(self.conv2(y))
+        return self.conv2_act(x + y)
+
+
+class Net(nn.Module):
+    """net.py:46-110: 119->256 stem, 40 residual blocks, policy head (2086 log-probs), value head."""
+
+    def __init__(self, num_channels=256, resblocks_num=40):
+        super().__init__()
+        self.input_channels = PLAYS * PIECES
+        self.conv_block = nn.Conv2d(self.input_channels, num_channels, kernel_size=(3, 3), stride=(1, 1), padding=1)
+        self.conv_block_bn = nn.BatchNorm2d(num_channels)
+        self.conv_block_act = nn.ReLU()
+        self.res_blocks = nn.ModuleList([ResBlock(num_channels=num_channels) for _ in range(resblocks_num)])
+        self.policy_conv = nn.Conv2d(num_channels, PLAYS, kernel_size=(1, 1), stride=(1, 1))
+        self.policy_bn = nn.BatchNorm2d(PLAYS)
+        self.policy_act = nn.ReLU()
+        self.policy_fc = nn.Linear(PLAYS * 10 * 9, N_ACTIONS)
+        self.value_conv = nn.Conv2d(num_channels, PIECES, kernel_size=(1, 1), stride=(1, 1))
+        self.value_bn = nn.BatchNorm2d(PIECES)
+        self.value_act1 = nn.ReLU()
+        self.value_fc1 = nn.Linear(PIECES * 10 * 9, 256)
+        self.value_act2 = nn.ReLU()
+        self.value_fc2 = nn.Linear(256, 1)
+
+    def forward(self, x):
+        x = x.view(x.shape[0], -1, 10, 9)
+        x = self.conv_block_act(self.conv_block_bn(self.conv_block(x)))
+        for block in self.res_blocks:
+            x = block(x)
+        policy = self.policy_act(self.policy_bn(self.policy_conv(x)))
+        policy = self.policy_fc(torch.reshape(policy, [-1, PLAYS * 10 * 9]))
+        policy = F.log_softmax(policy, dim=1)
+        value = self.value_act1(self.value_bn(self.value_conv(x)))
+        value = self.value_act2(self.value_fc1(torch.reshape(value, [-1, PIECES * 10 * 9])))
+        value = torch.tanh(self.value_fc2(value))
+        return policy, value
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm folded into the preceding convolution (fp32 arithmetic)."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return w * scale.view(-1, 1, 1, 1), (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+
+
+class BatchedEvaluator:
+    """bf16 lockstep-batch forward of a :class:`Net` (Net.forward, net.py:82-110).
+
+    ``__call__(planes, leaf_boards) -> (logits fp32 (G,2086), POLICY_LOGITS, values fp32 (G,))``
+    which is the evaluator protocol of :class:`search.LockstepSearch`.
+    """
+
+    def __init__(self, net: Net, device="cuda", dtype=torch.bfloat16, fused_epilogue: bool = True):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.fused = fused_epilogue
+        self.n_evals = 0
+        self.refresh(net)
+
+    @torch.no_grad()
+    def refresh(self, net: Net) -> None:
+        """(Re)fold the weights of ``net`` (call after a training update)."""
+        dev, dt = self.device, self.dtype
+        cl = torch.channels_last
+
+        def conv_params(conv, bn):
+            w, b = _fold(conv, bn)
+            return w.to(dev, dt).contiguous(memory_format=cl), b.to(dev, dt)
+
+        self.stem = conv_params(net.conv_block, net.conv_block_bn)
+        self.blocks = [(conv_params(rb.conv1, rb.conv1_bn), conv_params(rb.conv2, rb.conv2_bn))
+                       for rb in net.res_blocks]
+        # both 1x1 heads in one convolution: 17 policy + 7 value channels
+        pw, pb = _fold(net.policy_conv, net.policy_bn)
+        vw, vb = _fold(net.value_conv, net.value_bn)
+        self.heads_w = torch.cat([pw, vw], 0).to(dev, dt).contiguous(memory_format=cl)
+        self.heads_b = torch.cat([pb, vb], 0).to(dev, dt)
+        self.policy_fc = (net.policy_fc.weight.detach().to(dev, dt), net.policy_fc.bias.detach().to(dev, torch.float32))
+        self.value_fc1 = (net.value_fc1.weight.detach().to(dev, dt), net.value_fc1.bias.detach().to(dev, dt))
+        self.value_fc2 = (net.value_fc2.weight.detach().to(dev, torch.float32),
+                          net.value_fc2.bias.detach().to(dev, torch.float32))
+
+    def _conv_relu(self, x, wb):
+        w, b = wb
+        if self.fused:
+            return torch.cudnn_convolution_relu(x, w, b, (1, 1), (1, 1), (1, 1), 1)
+        return F.relu_(F.conv2d(x, w, b, padding=1))
+
+    def _conv_add_relu(self, x, wb, skip):
+        w, b = wb
+        if self.fused:
+            return torch.cudnn_convolution_add_relu(x, w, skip, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
+        return F.relu_(F.conv2d(x, w, b, padding=1).add_(skip))
+
+    @torch.no_grad()
+    def forward(self, planes: torch.Tensor):
+        g = planes.shape[0]
+        x = planes.view(g, PLAYS * PIECES, 10, 9).contiguous(memory_format=torch.channels_last)
+        x = self._conv_relu(x, self.stem)
+        for c1, c2 in self.blocks:
+            y = self._conv_relu(x, c1)
+            x = self._conv_add_relu(y, c2, x)
+        h = F.relu_(F.conv2d(x, self.heads_w, self.heads_b))  # (g, 24, 10, 9)
+        hp = h[:, :PLAYS].reshape(g, PLAYS * 90)               # NCHW flatten order, net.py:97
+        hv = h[:, PLAYS:].reshape(g, PIECES * 90)
+        logits = F.linear(hp, self.policy_fc[0]).float() + self.policy_fc[1]
+        v = F.relu_(F.linear(hv, *self.value_fc1)).float()
+        v = torch.tanh(F.linear(v, *self.value_fc2)).view(g)
+        return logits, v
+
+    def __call__(self, planes, leaf_boards=None):
+        logits, v = self.forward(planes)
+        self.n_evals += planes.shape[0]
+        return logits, _lib.POLICY_LOGITS, v
+
+
+class PolicyValueNet:
+    """Same constructor, attributes and methods as the reference class (net.py:113-247) for the
+    self-play path: ``policy_value_net`` (an nn.Module with the reference state_dict keys),
+    ``policy_value(state_batch)``, ``policy_value_fn(board)``, ``save_model(path)``."""
+
+    def __init__(self, model=None, use_gpu=True, num_channels=256, resblocks_num=40):
+        self.use_gpu = use_gpu
+        self.l2_const = 2e-3
+        self.device = torch.device("cuda") if (use_gpu and torch.cuda.is_available()) else torch.device("cpu")
+        self.policy_value_net = Net(num_channels, resblocks_num).to(self.device)
+        self.optimizer = torch.optim.Adam(self.policy_value_net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                                          weight_decay=self.l2_const)
+        if model:
+            self.policy_value_net.load_state_dict(torch.load(model, map_location=self.device))
+        self._evaluator = None
+
+    def evaluator(self, **kw) -> BatchedEvaluator:
+        """The lockstep-batch bf16 evaluator over the current weights (CUDA only, no fallback)."""
+        if self.device.type != "cuda":
+            raise _lib.CczError("BatchedEvaluator needs a CUDA device; there is no CPU fallback")
+        if self._evaluator is None:
+            self.policy_value_net.eval()
+            self._evaluator = BatchedEvaluator(self.policy_value_net, self.device, **kw)
+        return self._evaluator
+
+    def policy_value(self, state_batch):
+        """net.py:138-148: (act_probs ndarray (N,2086), value ndarray (N,1)) for a state batch."""
+        self.policy_value_net.eval()
+        if not isinstance(state_batch, torch.Tensor):
+            state_batch = torch.tensor(np.asarray(state_batch), dtype=torch.float)
+        state_batch = state_batch.to(self.device, torch.float32)
+        with torch.no_grad():
+            log_act_probs, value = self.policy_value_net(state_batch)
+        return np.exp(log_act_probs.cpu().numpy()), value.cpu().numpy()
+
+    def policy_value_fn(self, board, red_states=None, black_states=None):
+        """net.py:151-205 for ONE position given as a 96-byte board record (or an object with
+        ``.record()``): ``(zip(legal_ids, probs[legal_ids]), value ndarray (1,1))``.  Legal ids and
+        the input planes come from the CUDA kernel (ccz_movegen_encode); the forward runs in bf16."""
+        rec = board.record() if hasattr(board, "record") else board
+        boards = torch.as_tensor(np.ascontiguousarray(rec, dtype=np.uint8).reshape(1, 96)).to(self.device)
+        ids, counts, _, planes = _lib.movegen_encode(boards)
+        logits, v = self.evaluator().forward(planes)
+        probs = torch.softmax(logits, dim=1)[0].cpu().numpy()
+        legal = ids[0, : int(counts[0])].cpu().numpy().astype(np.int64)
+        return zip(legal.tolist(), probs[legal]), v.cpu().numpy().reshape(1, 1)
+
+    def save_model(self, model_file):
+        torch.save(self.policy_value_net.state_dict(), model_file)

@@ -51,9 +51,12 @@ class LockstepSearch:
     def root_boards(self) -> torch.Tensor:
         return self.arena.root_boards
 
-    def reset(self) -> None:
-        """Every game back to the start position with a fresh root (mcts.py:94, game.py:148)."""
-        _lib.mcts_reset(self.arena)
+    def reset(self, mask=None) -> None:
+        """Games back to the start position with a fresh root (mcts.py:94, game.py:148); ``mask``
+        (uint8 per game) restricts the reset to finished slots."""
+        if mask is not None:
+            mask = torch.as_tensor(mask, dtype=torch.uint8).to(self.device).contiguous()
+        _lib.mcts_reset(self.arena, mask)
 
     def set_roots(self, records) -> None:
         """History-less root positions from (G,96) board records; trees are dropped."""

@@ -1,0 +1,184 @@
+"""Lockstep self-play over thousands of concurrent games: the device counterpart of
+``Game.start_self_play`` + ``MCTS_AI.get_action`` (game.py:133-237, mcts.py:203-233).
+
+Every game slot follows the reference's per-game procedure:
+  * temperature 1.0 for the first 30 moves, then max(0.1, temp*0.5)            (game.py:159)
+  * n_playout playouts on the (reused) tree, pi = softmax(log(N+1e-10)/temp)    (mcts.py:150-166)
+  * move ~ Choice(acts, p = 0.75*pi + 0.25*Dirichlet(0.2)); the noise touches the move choice
+    only, the stored target is the un-noised pi                                (mcts.py:216-224)
+  * the sample (pi, side to move) is recorded and the history updated BEFORE the move is pushed
+    (game.py:196-201); the game ends on is_game_over() or is_tie()             (game.py:208)
+  * z = +1/-1 per recorded side when outcome() has a winner, else 0            (game.py:213-219)
+Noise is host-injected from a seeded NumPy Generator (one stream per engine, ``seed + rank`` in
+multi-GPU runs); ``deterministic=True`` switches noise off and takes the first most-visited move,
+which is the mode the parity tests compare against the reference's search.
+Finished slots are refilled from the start position immediately, so all slots stay in lockstep.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable
+
+import numpy as np
+import torch
+
+from . import _lib
+from .search import LockstepSearch, visit_softmax
+from .tools import outcome_winner_flags
+
+EPS, ALPHA = 0.25, 0.2  # parameters.py:10-12
+
+
+@dataclasses.dataclass
+class GameRecord:
+    """One finished game in sparse form.  ``boards[i]`` is the position searched at move i (the
+    record BEFORE the i-th move was pushed); ``acts[i]``/``probs[i]`` the un-noised visit
+    distribution over the root children; ``turns[i]`` the side to move (True = RED);
+    ``moves[i]`` the action id played; ``winner`` True/False/None; ``z[i]`` as in game.py:213-219."""
+
+    boards: np.ndarray          # (T, 96) uint8
+    acts: list                  # T arrays int16 (n_i,)
+    probs: list                 # T arrays float64 (n_i,)
+    turns: np.ndarray           # (T,) bool
+    moves: np.ndarray           # (T,) int16
+    winner: object
+    z: np.ndarray               # (T,) float64
+    final_flags: int
+    slot: int = -1
+
+    def __len__(self):
+        return int(self.moves.shape[0])
+
+
+class SelfPlayEngine:
+    def __init__(self, evaluator: Callable, n_games: int, n_playout: int = 400, c_puct: float = 5.0,
+                 temp: float = 1.0, node_cap: int | None = None, device="cuda", seed: int = 0,
+                 deterministic: bool = False, max_game_moves: int | None = None):
+        self.evaluator = evaluator
+        self.n_games, self.n_playout = int(n_games), int(n_playout)
+        self.temp = float(temp)
+        self.deterministic = bool(deterministic)
+        self.max_game_moves = max_game_moves
+        if node_cap is None:
+            # every playout adds at most one expansion of <= 119 children; reuse keeps a sub-tree.
+            node_cap = max(4096, int(self.n_playout * 64 * 2))
+        self.search = LockstepSearch(n_games, node_cap=node_cap, device=device, c_puct=c_puct)
+        self.rng = np.random.default_rng(seed)
+        self.device = self.search.device
+        g = self.n_games
+        self.move_count = np.zeros(g, dtype=np.int64)          # moves already played in each slot
+        self._boards = [[] for _ in range(g)]
+        self._acts = [[] for _ in range(g)]
+        self._probs = [[] for _ in range(g)]
+        self._turns = [[] for _ in range(g)]
+        self._moves = [[] for _ in range(g)]
+        # pinned staging for the per-move read-back / upload
+        pin = dict(pin_memory=True)
+        self._h_acts = torch.empty((g, _lib.MAX_MOVES), dtype=torch.int16, **pin)
+        self._h_visits = torch.empty((g, _lib.MAX_MOVES), dtype=torch.int32, **pin)
+        self._h_counts = torch.empty((g,), dtype=torch.int16, **pin)
+        self._h_boards = torch.empty((g, _lib.BOARD_BYTES), dtype=torch.uint8, **pin)
+        self._h_flags = torch.empty((g,), dtype=torch.uint8, **pin)
+        self._h_chosen = torch.empty((g,), dtype=torch.int16, **pin)
+        self._d_chosen = torch.empty((g,), dtype=torch.int16, device=self.device)
+        self._d_mask = torch.empty((g,), dtype=torch.uint8, device=self.device)
+        self._h_mask = torch.empty((g,), dtype=torch.uint8, **pin)
+        self._flag_out = (torch.empty((g, _lib.MAX_MOVES), dtype=torch.int16, device=self.device),
+                          torch.empty((g,), dtype=torch.int16, device=self.device),
+                          torch.empty((g,), dtype=torch.uint8, device=self.device), None)
+        self.total_moves = 0
+        self.total_games = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ------------------------------------------------------------------------------------
+    def current_temps(self) -> np.ndarray:
+        """game.py:159 with move_count already incremented for the move being chosen."""
+        mc = self.move_count + 1
+        return np.where(mc <= 30, self.temp, max(0.1, self.temp * 0.5))
+
+    def _choose(self, acts: np.ndarray, probs: np.ndarray) -> int:
+        if self.deterministic:
+            return int(acts[int(np.argmax(probs))])
+        p = (1 - EPS) * probs + EPS * self.rng.dirichlet(ALPHA * np.ones(len(probs)))
+        return int(self.rng.choice(acts, p=p / p.sum()))
+
+    def play_move(self) -> list[GameRecord]:
+        """One lockstep move in every slot; returns the games that finished with it."""
+        s = self.search
+        s.run(self.evaluator, self.n_playout)
+        acts_d, visits_d, counts_d = s.root_visits()
+        self._h_acts.copy_(acts_d, non_blocking=True)
+        self._h_visits.copy_(visits_d, non_blocking=True)
+        self._h_counts.copy_(counts_d, non_blocking=True)
+        self._h_boards.copy_(s.root_boards, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        s.check_status()
+        self.d2h_bytes += sum(t.numel() * t.element_size() for t in
+                              (self._h_acts, self._h_visits, self._h_counts, self._h_boards))
+        acts_np, visits_np = self._h_acts.numpy(), self._h_visits.numpy()
+        counts_np, boards_np = self._h_counts.numpy(), self._h_boards.numpy()
+        temps = self.current_temps()
+        chosen = self._h_chosen.numpy()
+        dense = np.zeros(_lib.N_ACTIONS)
+        for g in range(self.n_games):
+            n = int(counts_np[g])
+            if n <= 0:
+                raise _lib.CczError(f"game {g}: root has no children after search")
+            a = acts_np[g, :n].copy()
+            p = visit_softmax(visits_np[g, :n], float(temps[g]))
+            mv = self._choose(a, p)                             # mcts.py:216-224 (un-normalised probs)
+            dense[:] = 0.0                                      # mcts.py:212-215
+            dense[a] = p
+            p = (dense / np.sum(dense))[a]                      # game.py:187-190, same summation order
+            chosen[g] = mv
+            self._boards[g].append(boards_np[g].copy())
+            self._acts[g].append(a)
+            self._probs[g].append(p)
+            self._turns[g].append(bool(boards_np[g, 90]))
+            self._moves[g].append(mv)
+        self.move_count += 1
+        self.total_moves += self.n_games
+        self._d_chosen.copy_(self._h_chosen, non_blocking=True)
+        self.h2d_bytes += self._h_chosen.numel() * 2
+        s.advance(self._d_chosen)
+        # terminal test on the new root positions (game.py:208): flags straight from K1
+        _lib.movegen_encode(s.root_boards, planes=False, out=self._flag_out)
+        self._h_flags.copy_(self._flag_out[2], non_blocking=True)
+        self._h_boards.copy_(s.root_boards, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.d2h_bytes += self._h_flags.numel() + self._h_boards.numel()
+        flags = self._h_flags.numpy()
+        over = (flags & (_lib.FLAG_TIE_MASK | _lib.FLAG_NOMOVES)) != 0
+        if self.max_game_moves is not None:
+            over |= self.move_count >= self.max_game_moves
+        finished = []
+        if over.any():
+            mask = self._h_mask.numpy()
+            mask[:] = over
+            for g in np.nonzero(over)[0]:
+                finished.append(self._finish(int(g), int(flags[g]), bool(self._h_boards.numpy()[g, 90])))
+            self._d_mask.copy_(self._h_mask, non_blocking=True)
+            self.h2d_bytes += self.n_games
+            s.reset(self._d_mask)
+            self.total_games += len(finished)
+        return finished
+
+    def _finish(self, g: int, flags: int, turn_red: bool) -> GameRecord:
+        winner = outcome_winner_flags(flags, turn_red) if (flags & (_lib.FLAG_TIE_MASK | _lib.FLAG_NOMOVES)) else None
+        turns = np.array(self._turns[g], dtype=bool)
+        z = np.zeros(len(turns), dtype=np.float64)
+        if winner is not None:
+            z[:] = np.where(turns == winner, 1.0, -1.0)
+        rec = GameRecord(boards=np.stack(self._boards[g]), acts=self._acts[g], probs=self._probs[g], turns=turns,
+                         moves=np.array(self._moves[g], dtype=np.int16), winner=winner, z=z, final_flags=flags,
+                         slot=g)
+        self._boards[g], self._acts[g], self._probs[g], self._turns[g], self._moves[g] = [], [], [], [], []
+        self.move_count[g] = 0
+        return rec
+
+    def play(self, n_moves: int) -> list[GameRecord]:
+        out = []
+        for _ in range(n_moves):
+            out.extend(self.play_move())
+        return out

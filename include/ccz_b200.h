@@ -107,9 +107,9 @@ int ccz_board_push(uint8_t *d_boards, const int16_t *d_move_ids, int n, uint64_t
  * the record, earlier entries = a sentinel that matches nothing). */
 int ccz_board_keys_init(const uint8_t *d_boards, int n, uint64_t *d_keys, ccz_stream_t s);
 
-/* Reset every tree to a single unvisited root (Node(None, 1.0), mcts.py:94) over the start
- * position. */
-int ccz_mcts_reset(const ccz_arena *a, ccz_stream_t s);
+/* Reset trees to a single unvisited root (Node(None, 1.0), mcts.py:94) over the start position
+ * (game.py:148).  d_mask NULL = every game, else only games with d_mask[g] != 0 (slot refill). */
+int ccz_mcts_reset(const ccz_arena *a, const uint8_t *d_mask /*[n_games] or NULL*/, ccz_stream_t s);
 
 /* One selection pass per game: descend by PUCT from the root to a leaf, replaying the moves.
  * Writes the leaf position and the leaf's local node index. */

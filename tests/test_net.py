@@ -1,0 +1,84 @@
+"""Network parity.  CPU: the fp32 oracle and the product ``Net`` reproduce the UNMODIFIED reference
+net.Net outputs stored in tests/golden/net_reference.npz; BN folding is exact in fp32.  GPU: the bf16
+BatchedEvaluator stays within the north-star tolerance (1e-2 abs on probabilities and value)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_oracle
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "net_reference.npz"))
+
+
+def _product_net(perturbed: bool):
+    from chinesechesszero_b200.net import Net
+
+    torch.manual_seed(0)
+    net = Net()
+    if perturbed:
+        net_oracle.perturb_(net.state_dict(), seed=1)
+    return net.eval()
+
+
+@pytest.mark.parametrize("name", ["seed0", "perturbed"])
+def test_oracle_and_product_net_match_reference_golden(gold, name):
+    net = _product_net(name == "perturbed")
+    x = net_oracle.search_planes(gold["records"])
+    logp_o, v_o = net_oracle.forward(net.state_dict(), x)
+    # same machine -> bit-equal; other CPUs may reorder fp32 sums slightly
+    assert np.allclose(logp_o.numpy(), gold[f"{name}_logp"], atol=2e-5)
+    assert np.allclose(v_o.numpy(), gold[f"{name}_value"], atol=2e-5)
+    with torch.no_grad():
+        logp_p, v_p = net(x)
+    assert np.allclose(logp_p.numpy(), gold[f"{name}_logp"], atol=2e-5)
+    assert np.allclose(v_p.numpy(), gold[f"{name}_value"], atol=2e-5)
+
+
+def test_state_dict_keys_are_the_reference_ones():
+    net = _product_net(False)
+    keys = list(net.state_dict().keys())
+    assert keys[0] == "conv_block.weight" and "res_blocks.39.conv2_bn.running_var" in keys
+    assert "policy_fc.weight" in keys and "value_fc2.bias" in keys
+    assert sum(p.numel() for p in net.parameters()) == 50_883_979
+
+
+def test_bn_folding_is_exact_in_fp32_on_cpu():
+    from chinesechesszero_b200.net import BatchedEvaluator, Net
+
+    torch.manual_seed(3)
+    net = Net(num_channels=32, resblocks_num=3)
+    net_oracle.perturb_(net.state_dict(), seed=9)
+    net.eval()
+    ev = BatchedEvaluator(net, device="cpu", dtype=torch.float32, fused_epilogue=False)
+    x = torch.rand(5, 17, 7, 10, 9)
+    logits, v = ev.forward(x)
+    logp_o, v_o = net_oracle.forward(net.state_dict(), x)
+    assert torch.allclose(torch.log_softmax(logits, 1), logp_o, atol=1e-4)
+    assert torch.allclose(v, v_o.view(-1), atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["seed0", "perturbed"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_bf16_evaluator_within_tolerance(gold, name, fused):
+    from chinesechesszero_b200 import _lib
+    from chinesechesszero_b200.net import BatchedEvaluator
+
+    net = _product_net(name == "perturbed").cuda()
+    ev = BatchedEvaluator(net, fused_epilogue=fused)
+    boards = torch.from_numpy(gold["records"]).cuda()
+    _, _, _, planes = _lib.movegen_encode(boards)
+    logits, v = ev.forward(planes)
+    probs = torch.softmax(logits, 1).cpu().numpy()
+    ref_p = np.exp(gold[f"{name}_logp"])
+    # north-star tolerance: 1e-2 abs on policy and value in bf16
+    assert np.abs(probs - ref_p).max() < 1e-2
+    assert np.abs(v.cpu().numpy() - gold[f"{name}_value"].reshape(-1)).max() < 1e-2
+    # tighter sanity bound so the check is not vacuous for near-uniform policies
+    logp = torch.log_softmax(logits, 1).cpu().numpy()
+    assert np.abs(logp - gold[f"{name}_logp"]).max() < 5e-2
