@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the self-play hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            own arm (CUDA kernels + bf16 net)
+  python bench.py --impl reference [--steps K] [--warmup W]      reference arm (CPU port of collect.py)
+  torchrun --nproc-per-node N ... bench.py --gpus N ...          one rank per GPU, games sharded
+
+A *step* is one lockstep self-play move: n_playout (400) playouts in each of G (4096) concurrent
+games per GPU -- select, movegen+encode, one bf16 net forward over the whole leaf batch, expand +
+backup -- followed by move choice, tree re-rooting, terminal test and slot refill.
+Prints ONE JSON line (see DESIGN.md "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "self-play moves/sec at 400 playouts"
+UNIT = "moves/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU (configs[2]: 4096)")
+    ap.add_argument("--playouts", type=int, default=400)
+    ap.add_argument("--node-cap", type=int, default=65536)
+    ap.add_argument("--movegen-positions", type=int, default=1 << 20)
+    ap.add_argument("--no-movegen", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-moves", type=int, default=1, help="moves of the CPU-port sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return self
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(n_moves: int, n_playout: int):
+    """The reference's collect.py path on the host cores (oracle port; kind "port")."""
+    from oracle import collect_oracle
+
+    cores = os.cpu_count() or 1
+    mps, secs, evals = collect_oracle.time_moves(n_moves, n_playout=n_playout, threads=cores)
+    return {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n_moves} move(s) of one self-play game from the start position, {n_playout} playouts "
+                      f"each, batch-1 fp32 forward per playout ({evals} evals, {secs:.1f} s); cchess replaced by the "
+                      "C-backed shim (favours the reference)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import collect_oracle
+
+    cores = os.cpu_count() or 1
+    sp = collect_oracle.PortedSelfPlay(n_playout=args.playouts, threads=cores)
+    warm = min(args.warmup, 1)  # one full CPU move is ~15 s: a single warm-up move pages everything in
+    for _ in range(warm):
+        sp.play_move()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sp.play_move()
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = (f"{args.steps} consecutive move(s) of one self-play game, {args.playouts} playouts each, tree reuse, "
+              f"batch-1 fp32 forward per playout on {cores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init net, torch.manual_seed(0))",
+        "config": {"workload": "reference collect.py path: one self-play game on CPU, random-init PolicyValueNet",
+                   "n_playout": args.playouts, "games": 1},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def bench_movegen(torch, _lib, n_positions: int, peaks):
+    """configs[1]: legal-move generation + plane encoding on ~1M perft-reachable positions."""
+    import numpy as np
+    from oracle import cchess_shim as cs  # only to build the synthetic position set
+
+    l3 = cs.collect_leaves(cs.start_record(), 3, 79666)
+    need = max(0, n_positions - l3.shape[0])
+    if need:
+        l4 = cs.collect_leaves(cs.start_record(), 4, 3290240)
+        pick = np.sort(np.random.default_rng(0).choice(l4.shape[0], size=need, replace=False))
+        recs = np.concatenate([l3, l4[pick]])
+    else:
+        recs = l3[:n_positions]
+    n = recs.shape[0]
+    boards = torch.from_numpy(recs).cuda()
+    ids = torch.empty((n, 128), dtype=torch.int16, device="cuda")
+    counts = torch.empty((n,), dtype=torch.int16, device="cuda")
+    flags = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    planes = torch.empty((n, 17, 7, 10, 9), dtype=torch.bfloat16, device="cuda")
+    out = (ids, counts, flags, planes)
+    for _ in range(3):
+        _lib.movegen_encode(boards, out=out)
+    times = []
+    for _ in range(10):
+        planes.view(torch.int16).fill_(-1)  # poison: 22 GB written, also flushes L2
+        ids.fill_(-1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.movegen_encode(boards, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    mean_legal = float(counts.float().mean())
+    bytes_per_pos = 21520 + 2 * mean_legal
+    avg = sum(times) / len(times)
+    gbs = n * bytes_per_pos / avg / 1e6
+    # movegen only (planes = NULL)
+    t2 = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.movegen_encode(boards, planes=False, out=(ids, counts, flags, None))
+        e1.record()
+        torch.cuda.synchronize()
+        t2.append(e0.elapsed_time(e1))
+    # end to end through the C ABI wrapper with HOST buffers (pinned), copies inside the timed region
+    m = min(n, 1 << 16)
+    h_boards = torch.from_numpy(recs[:m]).pin_memory()
+    h_planes = torch.empty((m, 17, 7, 10, 9), dtype=torch.bfloat16).pin_memory()
+    h_ids = torch.empty((m, 128), dtype=torch.int16).pin_memory()
+    h_counts = torch.empty((m,), dtype=torch.int16).pin_memory()
+    h_flags = torch.empty((m,), dtype=torch.uint8).pin_memory()
+    sub = (ids[:m], counts[:m], flags[:m], planes[:m])
+    e2e_t = []
+    for it in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d_boards = boards[:m]
+        d_boards.copy_(h_boards, non_blocking=True)
+        _lib.movegen_encode(d_boards, out=sub)
+        h_ids.copy_(sub[0], non_blocking=True)
+        h_counts.copy_(sub[1], non_blocking=True)
+        h_flags.copy_(sub[2], non_blocking=True)
+        h_planes.copy_(sub[3], non_blocking=True)
+        torch.cuda.synchronize()
+        if it:
+            e2e_t.append(time.perf_counter() - t0)
+    e2e_s = sum(e2e_t) / len(e2e_t)
+    return {
+        "workload": f"configs[1]: movegen + plane encode on {n} perft-3/4 positions from the start position",
+        "metric": "movegen positions/sec", "value": n / avg * 1e3, "unit": "positions/s",
+        "ms_per_launch": avg, "best_ms": min(times), "mean_legal_moves": mean_legal,
+        "movegen_only_positions_per_s": n / (sum(t2) / len(t2)) * 1e3,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                     "bytes_per_position": bytes_per_pos, "peak_source": peaks["source"]},
+        "e2e": {"value": m / e2e_s, "unit": "positions/s", "positions": m,
+                "h2d_bytes_per_step": m * 96, "d2h_bytes_per_step": m * (21420 + 256 + 3)},
+    }
+
+
+def run_own_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from chinesechesszero_b200 import _lib
+    from chinesechesszero_b200.net import FLOP_PER_POSITION, BatchedEvaluator, Net
+    from chinesechesszero_b200.selfplay import SelfPlayEngine
+
+    peaks = measured_peaks()
+    torch.manual_seed(0)  # same random-init weights on every rank (net.py:120 default init)
+    net = Net().cuda().eval()
+    base_eval = BatchedEvaluator(net)
+    G, P = args.games, args.playouts
+
+    # per-phase device timing of the lockstep step: events around the forward and around our kernels
+    class TimedEvaluator:
+        def __init__(self):
+            self.pairs = []
+            self.on = False
+
+        def __call__(self, planes, leaf_boards):
+            if not self.on:
+                return base_eval(planes, leaf_boards)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = base_eval(planes, leaf_boards)
+            e1.record()
+            self.pairs.append((e0, e1))
+            return out
+
+    ev = TimedEvaluator()
+    eng = SelfPlayEngine(ev, n_games=G, n_playout=P, node_cap=args.node_cap, seed=1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up: W full moves (device-resident path) + one host-path move -------------------
+    for _ in range(args.warmup):
+        eng.play_move_resident()
+    eng.play_move()
+    barrier()
+
+    # ---- timed region 1: `value`, everything resident in HBM --------------------------------
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    ev.on = True
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        eng.play_move_resident()
+    s1.record()
+    barrier()
+    ev.on = False
+    dev_ms = max_over_ranks(s0.elapsed_time(s1))
+    clocks = sampler.stop() if sampler else None
+    fwd_ms = [a.elapsed_time(b) for a, b in ev.pairs]
+    ev.pairs = []
+    fwd_avg = sum(fwd_ms) / len(fwd_ms)
+    n_fwd = len(fwd_ms)
+    eng.search.check_status()
+    value = world * G * args.steps / dev_ms * 1e3
+
+    # ---- timed region 2: `e2e`, host-facing API (D2H visit read-back, host move choice, H2D) ----
+    h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.play_move()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    eng.search.check_status()
+    e2e_value = world * G * args.steps / e2e_ms * 1e3
+    h2d = (eng.h2d_bytes - h2d0) / args.steps
+    d2h = (eng.d2h_bytes - d2h0) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    tflops = G * FLOP_PER_POSITION / fwd_avg / 1e9
+    peak_tf = peaks["bf16_tflops_sustained"]
+    step_share = fwd_avg * n_fwd / s0.elapsed_time(s1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic (random-init net, torch.manual_seed(0); games from the start position)",
+        "config": {
+            "workload": f"configs[2]: lockstep batched self-play, {G} concurrent games x {P} playouts per GPU, "
+                        "random-init 40x256 PolicyValueNet",
+            "games_per_gpu": G, "n_playout": P, "node_cap": args.node_cap, "parallelism": f"games sharded x{world}, "
+            "no collective on the hot path",
+            "l2": "per-layer activations 4096x256x90 bf16 = 189 MB > 126 MB L2 (inputs larger than L2)",
+            "step": "one lockstep move = n_playout x (select, movegen+encode, bf16 forward, expand+backup) + move "
+                    "choice + re-root + terminal test + slot refill",
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps,
+                "api": "SelfPlayEngine.play_move(): per-move visit counts / boards / flags read back to pinned host "
+                       "memory, host-side visit softmax + seeded Dirichlet choice, chosen moves uploaded"},
+        "gpu_launches": args.steps * (P * 3 + 4),
+        "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": tflops / peak_tf, "traffic": None,
+                     "kernel": "bf16 Net.forward over the leaf batch (cuDNN fused conv+bias(+skip)+ReLU, library)",
+                     "flop_per_launch": G * FLOP_PER_POSITION, "ms_per_launch": fwd_avg, "launches_timed": n_fwd,
+                     "share_of_step": step_share, "peak_source": peaks["source"] + " sustained"},
+        "clocks": clocks,
+        "evals_per_move": P,
+    }
+    if not args.no_movegen:
+        line["movegen"] = bench_movegen(torch, _lib, args.movegen_positions, peaks)
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_moves, P)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

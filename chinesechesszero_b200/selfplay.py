@@ -177,6 +177,59 @@ class SelfPlayEngine:
         self.move_count[g] = 0
         return rec
 
+    # ------------------------------------------------------------------------------------
+    def _resident_state(self):
+        if getattr(self, "_res", None) is None:
+            g, dev = self.n_games, self.device
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(self.rng.integers(1 << 62)))
+            self._res = dict(
+                gen=gen,
+                idx=torch.arange(_lib.MAX_MOVES, device=dev).view(1, -1),
+                move_count=torch.zeros(g, dtype=torch.int64, device=dev),
+                finished=torch.zeros((), dtype=torch.int64, device=dev),
+                last_pi=torch.zeros((g, _lib.MAX_MOVES), dtype=torch.float64, device=dev),
+                last_boards=torch.zeros((g, _lib.BOARD_BYTES), dtype=torch.uint8, device=dev),
+                chosen=torch.zeros(g, dtype=torch.int16, device=dev),
+            )
+        return self._res
+
+    def play_move_resident(self) -> None:
+        """The same lockstep move with every input and output resident in HBM: visit softmax,
+        seeded Dirichlet mix, sampling, advance, terminal test and slot refill all run on the device
+        with no host synchronisation (the per-move sample stays in device buffers).  This is the
+        path bench.py times for ``value``; ``play_move`` is the host-facing one timed for ``e2e``."""
+        s, r = self.search, self._resident_state()
+        g = self.n_games
+        s.run(self.evaluator, self.n_playout)
+        acts, visits, counts = s.root_visits()
+        valid = r["idx"] < counts.view(g, 1)
+        lo_temp = max(0.1, self.temp * 0.5)
+        temps = torch.where(r["move_count"] < 30, self.temp, lo_temp).to(torch.float64).view(g, 1)
+        x = torch.log(visits.to(torch.float64) + 1e-10) / temps
+        pi = torch.softmax(x.masked_fill(~valid, float("-inf")), dim=1)
+        if self.deterministic:
+            choice = torch.argmax(pi, dim=1, keepdim=True)
+        else:
+            gam = torch._standard_gamma(torch.full((g, _lib.MAX_MOVES), ALPHA, dtype=torch.float64, device=self.device),
+                                        generator=r["gen"]) * valid
+            mix = (1 - EPS) * pi + EPS * gam / gam.sum(dim=1, keepdim=True).clamp_min(1e-300)
+            choice = torch.multinomial(mix, 1, generator=r["gen"])
+        r["chosen"].copy_(acts.gather(1, choice).view(g))
+        r["last_pi"].copy_(pi)
+        r["last_boards"].copy_(s.root_boards)
+        s.advance(r["chosen"])
+        _lib.movegen_encode(s.root_boards, planes=False, out=self._flag_out)
+        over = (self._flag_out[2] & (_lib.FLAG_TIE_MASK | _lib.FLAG_NOMOVES)) != 0
+        mc = r["move_count"] + 1
+        if self.max_game_moves is not None:
+            over = over | (mc >= self.max_game_moves)
+        self._d_mask.copy_(over.to(torch.uint8))
+        s.reset(self._d_mask)
+        r["move_count"] = torch.where(over, torch.zeros_like(mc), mc)
+        r["finished"] += over.sum()
+        self.total_moves += g
+
     def play(self, n_moves: int) -> list[GameRecord]:
         out = []
         for _ in range(n_moves):
