@@ -61,7 +61,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.OUT
+    # CCZ_LIB points at an alternative build of the same library (debug / bisect builds)
+    return os.environ.get("CCZ_LIB") or _build.OUT
 
 
 def load() -> ctypes.CDLL:

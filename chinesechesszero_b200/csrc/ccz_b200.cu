@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <string>
 
 #include "ccz_movegen.cuh"
@@ -38,12 +39,65 @@ struct HostTables {
     int16_t flip_of[ccz::N_ACTIONS];
     uint64_t zkeys[16 * 90 + 1];
     uint8_t start[ccz::BOARD_BYTES];
+    uint16_t step_tab[ccz::STEP_TAB_ENTRIES];
     bool built = false;
 };
 HostTables g_tab;
 bool g_dev_ready[64] = {false};
 
 int sq_of(const char *s) { return (s[0] - 'a') + 9 * (s[1] - '0'); }
+
+// Step-piece move table for K1: kind = {pawn, knight, elephant, advisor, king} x {red, black};
+// per (kind, from-square) up to 8 entries `to | block << 7` (block = knight leg / elephant eye,
+// 127 = none) sorted by target square DESCENDING (cchess generation order), 0xFFFF-terminated.
+void build_step_table(uint16_t *tab) {
+    for (int kind = 0; kind < ccz::STEP_KINDS; ++kind) {
+        const int piece = kind / 2;
+        const bool black = kind & 1;
+        for (int sq = 0; sq < 90; ++sq) {
+            const int r = sq / 9, f = sq % 9;
+            int to[8], blk[8], m = 0;
+            auto add = [&](int rr, int ff, int b) {
+                if (rr < 0 || rr > 9 || ff < 0 || ff > 8) return;
+                to[m] = rr * 9 + ff;
+                blk[m++] = b;
+            };
+            auto in_palace = [&](int rr, int ff) {
+                return ff >= 3 && ff <= 5 && (black ? (rr >= 7 && rr <= 9) : (rr >= 0 && rr <= 2));
+            };
+            if (piece == 0) { // pawn: forward; sideways once across the river
+                add(r + (black ? -1 : 1), f, 127);
+                if (black ? r <= 4 : r >= 5) { add(r, f - 1, 127); add(r, f + 1, 127); }
+            } else if (piece == 1) { // knight: leg next to the knight along the long axis
+                static const int d[8][2] = {{2, 1}, {2, -1}, {-2, 1}, {-2, -1}, {1, 2}, {1, -2}, {-1, 2}, {-1, -2}};
+                for (auto &k : d) {
+                    const int lr = r + (k[0] == 2 ? 1 : k[0] == -2 ? -1 : 0), lf = f + (k[1] == 2 ? 1 : k[1] == -2 ? -1 : 0);
+                    add(r + k[0], f + k[1], lr * 9 + lf);
+                }
+            } else if (piece == 2) { // elephant: eye in the middle, never crosses the river
+                for (int a = -2; a <= 2; a += 4)
+                    for (int c = -2; c <= 2; c += 4) {
+                        const int rr = r + a;
+                        if (rr < 0 || rr > 9 || (black ? rr < 5 : rr > 4)) continue;
+                        add(rr, f + c, (r + a / 2) * 9 + f + c / 2);
+                    }
+            } else if (piece == 3) { // advisor
+                for (int a = -1; a <= 1; a += 2)
+                    for (int c = -1; c <= 1; c += 2)
+                        if (in_palace(r + a, f + c)) add(r + a, f + c, 127);
+            } else { // king
+                static const int d[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+                for (auto &k : d)
+                    if (in_palace(r + k[0], f + k[1])) add(r + k[0], f + k[1], 127);
+            }
+            for (int i = 0; i < m; ++i) // descending by target
+                for (int j = i + 1; j < m; ++j)
+                    if (to[j] > to[i]) { std::swap(to[i], to[j]); std::swap(blk[i], blk[j]); }
+            uint16_t *e = tab + (kind * 90 + sq) * ccz::STEP_SLOTS;
+            for (int i = 0; i < ccz::STEP_SLOTS; ++i) e[i] = i < m ? (uint16_t)(to[i] | (blk[i] << 7)) : 0xFFFF;
+        }
+    }
+}
 
 // The fixed 2086-entry action table (tools.py:172-272): per source square in rank-major order
 // the 9 same-file destinations by rank, the 8 same-rank destinations by file, then the knight
@@ -110,6 +164,7 @@ void build_tables() {
         t.start[54 + f] = 1 | 8;
     }
     t.start[ccz::OFF_TURN] = 1;
+    build_step_table(t.step_tab);
     t.built = (idx == ccz::N_ACTIONS);
 }
 
@@ -126,6 +181,7 @@ int ensure_device() {
     CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_flip_of, g_tab.flip_of, sizeof(g_tab.flip_of)));
     CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_zkeys, g_tab.zkeys, sizeof(g_tab.zkeys)));
     CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_start_board, g_tab.start, sizeof(g_tab.start)));
+    CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_step_tab, g_tab.step_tab, sizeof(g_tab.step_tab)));
     g_dev_ready[dev] = true;
     return 0;
 }
