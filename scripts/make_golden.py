@@ -39,6 +39,9 @@ if __name__ == "__main__":
     if what in ("mcts", "all"):
         from scripts import golden_mcts
         golden_mcts.main(GOLDEN)
+    if what in ("game", "all"):
+        from scripts import golden_game
+        golden_game.main(GOLDEN)
     if what in ("net", "all"):
         from scripts import golden_net
         golden_net.main(GOLDEN)
