@@ -47,56 +47,58 @@ bool g_dev_ready[64] = {false};
 
 int sq_of(const char *s) { return (s[0] - 'a') + 9 * (s[1] - '0'); }
 
-// Step-piece move table for K1: kind = {pawn, knight, elephant, advisor, king} x {red, black};
-// per (kind, from-square) up to 8 entries `to | block << 7` (block = knight leg / elephant eye,
-// 127 = none) sorted by target square DESCENDING (cchess generation order), 0xFFFF-terminated.
+// Step-piece move table for K1 (layout in ccz_movegen.cuh): per (piece kind, from-square) the
+// targets `to | block << 7` (block = knight leg / elephant eye, 127 = none) sorted by target square
+// DESCENDING (cchess generation order), 0xFFFF-terminated.
 void build_step_table(uint16_t *tab) {
-    for (int kind = 0; kind < ccz::STEP_KINDS; ++kind) {
-        const int piece = kind / 2;
-        const bool black = kind & 1;
-        for (int sq = 0; sq < 90; ++sq) {
-            const int r = sq / 9, f = sq % 9;
-            int to[8], blk[8], m = 0;
-            auto add = [&](int rr, int ff, int b) {
-                if (rr < 0 || rr > 9 || ff < 0 || ff > 8) return;
-                to[m] = rr * 9 + ff;
-                blk[m++] = b;
-            };
-            auto in_palace = [&](int rr, int ff) {
-                return ff >= 3 && ff <= 5 && (black ? (rr >= 7 && rr <= 9) : (rr >= 0 && rr <= 2));
-            };
-            if (piece == 0) { // pawn: forward; sideways once across the river
-                add(r + (black ? -1 : 1), f, 127);
-                if (black ? r <= 4 : r >= 5) { add(r, f - 1, 127); add(r, f + 1, 127); }
-            } else if (piece == 1) { // knight: leg next to the knight along the long axis
-                static const int d[8][2] = {{2, 1}, {2, -1}, {-2, 1}, {-2, -1}, {1, 2}, {1, -2}, {-1, 2}, {-1, -2}};
-                for (auto &k : d) {
-                    const int lr = r + (k[0] == 2 ? 1 : k[0] == -2 ? -1 : 0), lf = f + (k[1] == 2 ? 1 : k[1] == -2 ? -1 : 0);
-                    add(r + k[0], f + k[1], lr * 9 + lf);
-                }
-            } else if (piece == 2) { // elephant: eye in the middle, never crosses the river
-                for (int a = -2; a <= 2; a += 4)
-                    for (int c = -2; c <= 2; c += 4) {
-                        const int rr = r + a;
-                        if (rr < 0 || rr > 9 || (black ? rr < 5 : rr > 4)) continue;
-                        add(rr, f + c, (r + a / 2) * 9 + f + c / 2);
+    for (int i = 0; i < ccz::STEP_TAB_ENTRIES; ++i) tab[i] = 0xFFFF;
+    // piece: 0 pawn, 1 elephant, 2 advisor, 3 king (x colour), 4 knight
+    for (int piece = 0; piece < 5; ++piece)
+        for (int black = 0; black < (piece == 4 ? 1 : 2); ++black)
+            for (int sq = 0; sq < 90; ++sq) {
+                const int r = sq / 9, f = sq % 9;
+                int to[8], blk[8], m = 0;
+                auto add = [&](int rr, int ff, int b) {
+                    if (rr < 0 || rr > 9 || ff < 0 || ff > 8) return;
+                    to[m] = rr * 9 + ff;
+                    blk[m++] = b;
+                };
+                auto in_palace = [&](int rr, int ff) {
+                    return ff >= 3 && ff <= 5 && (black ? (rr >= 7 && rr <= 9) : (rr >= 0 && rr <= 2));
+                };
+                if (piece == 0) { // pawn: forward; sideways once across the river
+                    add(r + (black ? -1 : 1), f, 127);
+                    if (black ? r <= 4 : r >= 5) { add(r, f - 1, 127); add(r, f + 1, 127); }
+                } else if (piece == 4) { // knight: leg next to the knight along the long axis
+                    static const int d[8][2] = {{2, 1}, {2, -1}, {-2, 1}, {-2, -1}, {1, 2}, {1, -2}, {-1, 2}, {-1, -2}};
+                    for (auto &k : d) {
+                        const int lr = r + (k[0] == 2 ? 1 : k[0] == -2 ? -1 : 0);
+                        const int lf = f + (k[1] == 2 ? 1 : k[1] == -2 ? -1 : 0);
+                        add(r + k[0], f + k[1], lr * 9 + lf);
                     }
-            } else if (piece == 3) { // advisor
-                for (int a = -1; a <= 1; a += 2)
-                    for (int c = -1; c <= 1; c += 2)
-                        if (in_palace(r + a, f + c)) add(r + a, f + c, 127);
-            } else { // king
-                static const int d[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
-                for (auto &k : d)
-                    if (in_palace(r + k[0], f + k[1])) add(r + k[0], f + k[1], 127);
+                } else if (piece == 1) { // elephant: eye in the middle, never crosses the river
+                    for (int a = -2; a <= 2; a += 4)
+                        for (int c = -2; c <= 2; c += 4) {
+                            const int rr = r + a;
+                            if (rr < 0 || rr > 9 || (black ? rr < 5 : rr > 4)) continue;
+                            add(rr, f + c, (r + a / 2) * 9 + f + c / 2);
+                        }
+                } else if (piece == 2) { // advisor
+                    for (int a = -1; a <= 1; a += 2)
+                        for (int c = -1; c <= 1; c += 2)
+                            if (in_palace(r + a, f + c)) add(r + a, f + c, 127);
+                } else { // king
+                    static const int d[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+                    for (auto &k : d)
+                        if (in_palace(r + k[0], f + k[1])) add(r + k[0], f + k[1], 127);
+                }
+                for (int i = 0; i < m; ++i) // descending by target
+                    for (int j = i + 1; j < m; ++j)
+                        if (to[j] > to[i]) { std::swap(to[i], to[j]); std::swap(blk[i], blk[j]); }
+                uint16_t *e = piece == 4 ? tab + sq * 8
+                                         : tab + ccz::STEP_KNIGHT_ENTRIES + ((piece * 2 + black) * 90 + sq) * 4;
+                for (int i = 0; i < m; ++i) e[i] = (uint16_t)(to[i] | (blk[i] << 7));
             }
-            for (int i = 0; i < m; ++i) // descending by target
-                for (int j = i + 1; j < m; ++j)
-                    if (to[j] > to[i]) { std::swap(to[i], to[j]); std::swap(blk[i], blk[j]); }
-            uint16_t *e = tab + (kind * 90 + sq) * ccz::STEP_SLOTS;
-            for (int i = 0; i < ccz::STEP_SLOTS; ++i) e[i] = i < m ? (uint16_t)(to[i] | (blk[i] << 7)) : 0xFFFF;
-        }
-    }
 }
 
 // The fixed 2086-entry action table (tools.py:172-272): per source square in rank-major order
@@ -252,10 +254,21 @@ int ccz_movegen_encode(const uint8_t *d_boards, int n, int16_t *d_move_ids, int1
     if (int rc = ensure_device()) return rc;
     const int n_quads = (n + 3) / 4;
     int grid = (n_quads + ccz::MG_WARPS - 1) / ccz::MG_WARPS;
-    const int cap = sm_count() * 8;
+    const int cap = sm_count() * CCZ_MG_MIN_BLOCKS; // one resident wave; warps claim quads dynamically
     if (grid > cap) grid = cap;
+    static unsigned int *claim_base[64] = {nullptr};
+    static unsigned launch_no = 0;
+    int dev = 0;
+    CCZ_CUDA(cudaGetDevice(&dev));
+    if (!claim_base[dev]) {
+        // static smem (tables + per-warp scratch) wants the full shared-memory carve-out
+        cudaFuncSetAttribute(ccz::movegen_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        CCZ_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&claim_base[dev]), ccz::d_mg_counter));
+    }
+    unsigned int *claim = claim_base[dev] + (launch_no++ % ccz::MG_COUNTER_SLOTS);
+    CCZ_CUDA(cudaMemsetAsync(claim, 0, sizeof(unsigned int), s));
     ccz::movegen_encode_kernel<<<grid, ccz::MG_WARPS * 32, 0, s>>>(d_boards, n, d_move_ids, d_counts, d_flags,
-                                                                  static_cast<uint32_t *>(d_planes_bf16));
+                                                                  static_cast<uint32_t *>(d_planes_bf16), claim);
     return check_launch("movegen_encode_kernel");
 }
 

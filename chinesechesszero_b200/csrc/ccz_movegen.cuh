@@ -32,14 +32,19 @@ namespace ccz {
 #else
 #define CCZ_Q_UNROLL
 #endif
+#ifndef CCZ_MG_MIN_BLOCKS
+#define CCZ_MG_MIN_BLOCKS 4
+#endif
 constexpr int MG_WARPS = 8;
 constexpr int WORDS_PER_POS = PLANE_ELEMS / 2; // 5355 32-bit words (two bf16) per position
-constexpr int STEP_KINDS = 10;                 // {pawn, knight, elephant, advisor, king} x {red, black}
-constexpr int STEP_SLOTS = 8;
-constexpr int STEP_TAB_ENTRIES = STEP_KINDS * 90 * STEP_SLOTS;
-
-// (kind, from) -> up to 8 entries, target DESCENDING: to | block_square << 7 (127 = none); 0xFFFF = end
+// Step-piece table: knights [90][8] (colour independent), then {pawn, elephant, advisor, king} x
+// {red, black} [8][90][4]; entries target DESCENDING: to | block_square << 7 (127 = none), 0xFFFF = end
+constexpr int STEP_KNIGHT_ENTRIES = 90 * 8;
+constexpr int STEP_TAB_ENTRIES = STEP_KNIGHT_ENTRIES + 8 * 90 * 4 + 8; // + 8 pad: the scan reads 8 slots
 __device__ __align__(16) uint16_t d_step_tab[STEP_TAB_ENTRIES];
+// quad-claim counters of the dynamic scheduler (one slot per in-flight launch, zeroed in-stream)
+constexpr int MG_COUNTER_SLOTS = 16;
+__device__ unsigned int d_mg_counter[MG_COUNTER_SLOTS];
 
 struct __align__(16) MgWarpSmem {
     uint8_t boards[4][BOARD_BYTES]; // 384
@@ -229,13 +234,14 @@ __device__ CCZ_MG_INLINE void movegen_one(MgWarpSmem &w, const uint8_t *B, const
         const uint32_t pc = B[from];
         const int ty = pc & 7;
         if (dir == 4) {
-            const int kind = (ty == PAWN ? 0 : ty - 3) * 2 + (red ? 0 : 1);
-            ent = s_step + (kind * 90 + from) * STEP_SLOTS;
+            const int kind4 = (ty == PAWN ? 0 : ty - 4) * 2 + (red ? 0 : 1);
+            const int nsl = ty == KNIGHT ? 8 : 4;
+            ent = ty == KNIGHT ? s_step + from * 8 : s_step + STEP_KNIGHT_ENTRIES + (kind4 * 90 + from) * 4;
 #pragma unroll
-            for (int i = 0; i < STEP_SLOTS; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 const uint32_t e = ent[i];
                 const int to = e & 127, blk = (e >> 7) & 127;
-                const bool good = e != 0xFFFFu && (blk == 127 || B[blk] == 0) && !own_piece(B[to], red);
+                const bool good = i < nsl && e != 0xFFFFu && (blk == 127 || B[blk] == 0) && !own_piece(B[to], red);
                 ok |= (uint32_t)good << i;
             }
             cnt = __popc(ok);
@@ -375,14 +381,16 @@ __device__ __forceinline__ void encode_quad(const MgWarpSmem &w, uint32_t *out, 
     }
 }
 
-__global__ void __launch_bounds__(MG_WARPS * 32)
+__global__ void __launch_bounds__(MG_WARPS * 32, CCZ_MG_MIN_BLOCKS)
 movegen_encode_kernel(const uint8_t *__restrict__ boards, int n, int16_t *__restrict__ move_ids,
-                      int16_t *__restrict__ counts, uint8_t *__restrict__ flags, uint32_t *__restrict__ planes) {
+                      int16_t *__restrict__ counts, uint8_t *__restrict__ flags, uint32_t *__restrict__ planes,
+                      unsigned int *__restrict__ claim) {
     __shared__ __align__(16) int16_t s_id_of[8100];
     __shared__ __align__(16) uint16_t s_step[STEP_TAB_ENTRIES];
     __shared__ MgWarpSmem s_w[MG_WARPS];
     for (int i = threadIdx.x; i < 8100 / 2; i += blockDim.x)
         reinterpret_cast<uint32_t *>(s_id_of)[i] = reinterpret_cast<const uint32_t *>(d_id_of)[i];
+    static_assert(STEP_TAB_ENTRIES % 8 == 0, "uint4 copy");
     for (int i = threadIdx.x; i < STEP_TAB_ENTRIES / 8; i += blockDim.x)
         reinterpret_cast<uint4 *>(s_step)[i] = reinterpret_cast<const uint4 *>(d_step_tab)[i];
     __syncthreads();
@@ -390,7 +398,12 @@ movegen_encode_kernel(const uint8_t *__restrict__ boards, int n, int16_t *__rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     MgWarpSmem &w = s_w[warp];
     const int n_quads = (n + 3) >> 2;
-    for (int quad = blockIdx.x * MG_WARPS + warp; quad < n_quads; quad += gridDim.x * MG_WARPS) {
+    // persistent warps claim quads from a global counter: one resident wave, no tail imbalance
+    while (true) {
+        int quad = 0;
+        if (lane == 0) quad = (int)atomicAdd(claim, 1u);
+        quad = __shfl_sync(0xffffffffu, quad, 0);
+        if (quad >= n_quads) break;
         const int base = quad * 4;
         const int nb = min(4, n - base);
         if (lane < nb * 6)
