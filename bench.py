@@ -148,19 +148,11 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 def bench_movegen(torch, _lib, n_positions: int, peaks):
     """configs[1]: legal-move generation + plane encoding on ~1M perft-reachable positions."""
-    import numpy as np
-    from oracle import cchess_shim as cs  # only to build the synthetic position set
+    from chinesechesszero_b200 import positions
 
-    l3 = cs.collect_leaves(cs.start_record(), 3, 79666)
-    need = max(0, n_positions - l3.shape[0])
-    if need:
-        l4 = cs.collect_leaves(cs.start_record(), 4, 3290240)
-        pick = np.sort(np.random.default_rng(0).choice(l4.shape[0], size=need, replace=False))
-        recs = np.concatenate([l3, l4[pick]])
-    else:
-        recs = l3[:n_positions]
-    n = recs.shape[0]
-    boards = torch.from_numpy(recs).cuda()
+    boards = positions.bench_positions(n_positions, seed=0)  # generated on the device by K1 + K2
+    n = boards.shape[0]
+    recs_host = boards[: min(n, 1 << 16)].cpu()
     ids = torch.empty((n, 128), dtype=torch.int16, device="cuda")
     counts = torch.empty((n,), dtype=torch.int16, device="cuda")
     flags = torch.empty((n,), dtype=torch.uint8, device="cuda")
@@ -193,7 +185,7 @@ def bench_movegen(torch, _lib, n_positions: int, peaks):
         t2.append(e0.elapsed_time(e1))
     # end to end through the C ABI wrapper with HOST buffers (pinned), copies inside the timed region
     m = min(n, 1 << 16)
-    h_boards = torch.from_numpy(recs[:m]).pin_memory()
+    h_boards = recs_host[:m].pin_memory()
     h_planes = torch.empty((m, 17, 7, 10, 9), dtype=torch.bfloat16).pin_memory()
     h_ids = torch.empty((m, 128), dtype=torch.int16).pin_memory()
     h_counts = torch.empty((m,), dtype=torch.int16).pin_memory()
@@ -228,18 +220,15 @@ def bench_movegen(torch, _lib, n_positions: int, peaks):
 
 
 def run_own_arm(args):
-    import numpy as np
     import torch
-    import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from chinesechesszero_b200 import distributed as D
+
+    rank, local_rank, world = D.shard_info()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D.init("nccl", device=torch.device("cuda", local_rank))
 
     from chinesechesszero_b200 import _lib
     from chinesechesszero_b200.net import FLOP_PER_POSITION, BatchedEvaluator, Net
@@ -268,19 +257,14 @@ def run_own_arm(args):
             return out
 
     ev = TimedEvaluator()
-    eng = SelfPlayEngine(ev, n_games=G, n_playout=P, node_cap=args.node_cap, seed=1234 + rank)
+    eng = SelfPlayEngine(ev, n_games=G, n_playout=P, node_cap=args.node_cap, seed=D.rank_seed(1234, rank))
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.max_over_ranks(ms, device="cuda")
 
     # ---- warm-up: W full moves (device-resident path) + one host-path move -------------------
     for _ in range(args.warmup):
@@ -322,9 +306,8 @@ def run_own_arm(args):
     d2h = (eng.d2h_bytes - d2h0) / args.steps
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        D.barrier()
+        D.shutdown()
         return
 
     tflops = G * FLOP_PER_POSITION / fwd_avg / 1e9
@@ -361,9 +344,8 @@ def run_own_arm(args):
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_moves, P)
     print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.barrier()
+    D.shutdown()
 
 
 def main():

@@ -96,3 +96,15 @@ def test_start_boards_kernel():
 
     b = _lib.boards_start(5).cpu().numpy()
     assert np.array_equal(b, np.tile(cs.start_record(), (5, 1)))
+
+
+def test_device_perft_counts_and_order():
+    """GPU breadth-first expansion (K1 + K2): level sizes are the published perft numbers and the
+    perft-3 level equals the oracle's leaves in generation order."""
+    from chinesechesszero_b200 import positions as dev_positions
+
+    levels = dev_positions.perft_levels(3)
+    assert [lv.shape[0] for lv in levels] == [44, 1920, 79666]
+    assert np.array_equal(levels[2].cpu().numpy(), positions.perft_leaves(3))
+    assert dev_positions.perft_count(4) == 3290240
+    assert dev_positions.perft_count(5) == 133312995
