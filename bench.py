@@ -23,8 +23,23 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "self-play moves/sec at 400 playouts"
+METRIC = "self-play moves/sec at 400 playouts"  # the playout count in the string follows --playouts
 UNIT = "moves/s"
+
+
+def metric_name(playouts: int) -> str:
+    return f"self-play moves/sec at {playouts} playouts"
+
+
+def ncu_traffic(kernel: str, units: int):
+    """dram read+write bytes per launch from the committed ncu capture (profiles/ncu_traffic.json),
+    scaled to `units`; None when no capture is recorded for the kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * units / t["positions_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def parse_args():
@@ -134,7 +149,7 @@ def run_reference_arm(args):
     sample = (f"{args.steps} consecutive move(s) of one self-play game, {args.playouts} playouts each, tree reuse, "
               f"batch-1 fp32 forward per playout on {cores} host threads")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args.playouts), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init net, torch.manual_seed(0))",
         "config": {"workload": "reference collect.py path: one self-play game on CPU, random-init PolicyValueNet",
@@ -212,7 +227,8 @@ def bench_movegen(torch, _lib, n_positions: int, peaks):
         "ms_per_launch": avg, "best_ms": min(times), "mean_legal_moves": mean_legal,
         "movegen_only_positions_per_s": n / (sum(t2) / len(t2)) * 1e3,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                     "frac": gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("movegen_encode_kernel", n),
+                     "algorithmic_bytes_per_launch": n * bytes_per_pos,
                      "bytes_per_position": bytes_per_pos, "peak_source": peaks["source"]},
         "e2e": {"value": m / e2e_s, "unit": "positions/s", "positions": m,
                 "h2d_bytes_per_step": m * 96, "d2h_bytes_per_step": m * (21420 + 256 + 3)},
@@ -314,7 +330,7 @@ def run_own_arm(args):
     peak_tf = peaks["bf16_tflops_sustained"]
     step_share = fwd_avg * n_fwd / s0.elapsed_time(s1)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(P), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic (random-init net, torch.manual_seed(0); games from the start position)",
         "config": {

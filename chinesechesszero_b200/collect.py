@@ -6,16 +6,20 @@ replay store, bump the game counter -- but plays ``n_games`` games concurrently 
 GPU (``selfplay.SelfPlayEngine``) and lets K8 do the densification.  Games are appended in the order
 they finish; each finished game becomes one ``game_{k}`` unit exactly like one reference iteration.
 
-Output: the ``states.npy / mcts.npy / winners.npy / meta.json`` layout the reference's trainer reads
-(train.py:95-100) via ``replay.NpyReplayWriter``; the ``data.h5`` container itself (collect.py:146-167)
-is the next row of SURVEY.md §8(f) -- no HDF5 library exists in this image.
+Outputs (both in the reference's layouts):
+  * ``<data_dir>/data.h5``  -- group ``game_{k}`` with ``states`` / ``mcts_probs`` (gzip) / ``winners`` and
+    the root attribute ``iters`` (collect.py:146-167), written by ``h5lite`` (no h5py/libhdf5 here);
+  * ``<data_dir>/states.npy, mcts.npy, winners.npy, meta.json`` -- what convert.py makes of that file and
+    what the trainer reads (convert.py:85-99, train.py:95-100).
+Multi-GPU: every rank writes its own ``<data_dir>/rank{r}/`` shard with disjoint ``game_{k}`` numbers
+(``distributed.global_game_index``); ``merge_h5_shards`` folds them into one file.
 """
 from __future__ import annotations
 
 import argparse
 import os
 
-from . import replay
+from . import distributed, h5lite, replay
 from .net import PolicyValueNet
 from .parameters import C_PUCT, DATA_DIR, MODEL_DIR, PLAYOUT
 from .selfplay import SelfPlayEngine
@@ -23,23 +27,29 @@ from .selfplay import SelfPlayEngine
 
 class CollectPipeline:
     def __init__(self, init_model=None, n_games=4096, n_playout=PLAYOUT, c_puct=C_PUCT, data_dir=DATA_DIR,
-                 states_mode="reference", seed=0, node_cap=None, max_game_moves=None, net_kwargs=None):
+                 states_mode="reference", seed=0, node_cap=None, max_game_moves=None, net_kwargs=None,
+                 write_h5=True, write_npy=True, rank=0, world=1):
         self.temp = 1.0
         self.n_playout = n_playout
         self.c_puct = c_puct
         self.init_model = init_model
         self.n_games = n_games
-        self.iters = 0
         self.episode_len = 0
         self.policy_value_net = None
         self.engine = None
-        self.data_dir = data_dir
+        self.rank, self.world = int(rank), int(world)
+        self.data_dir = data_dir if self.world == 1 else os.path.join(data_dir, f"rank{self.rank}")
+        self.data_path = os.path.join(self.data_dir, "data.h5")
         self.states_mode = states_mode
-        self.seed = seed
+        self.seed = distributed.rank_seed(seed, self.rank)
         self.node_cap = node_cap
         self.max_game_moves = max_game_moves
         self.net_kwargs = net_kwargs or {}
-        self.writer = replay.NpyReplayWriter(data_dir)
+        self.npy = replay.NpyReplayWriter(self.data_dir) if write_npy else None
+        self.h5 = h5lite.H5ReplayWriter(self.data_path) if write_h5 else None
+        # collect.py:39-45: the game counter continues from the file's ``iters`` attribute
+        self.local_games = self.h5.iters if (self.h5 is not None and self.world == 1) else 0
+        self.iters = self.local_games
 
     def load_model(self):
         """collect.py:47-62: load once; fall back to random init when the model cannot be loaded."""
@@ -60,20 +70,52 @@ class CollectPipeline:
         self.load_model()
         for rec in self.engine.play_move():
             states, probs, winners = replay.pack_game(rec, self.states_mode, device=self.engine.device)
-            self.writer.add(states, probs, winners)
+            if self.h5 is not None:
+                index = distributed.global_game_index(self.local_games, self.rank, self.world)
+                self.h5.add(states, probs, winners, index=index if self.world > 1 else None)
+            if self.npy is not None:
+                self.npy.add(states, probs, winners)
             self.episode_len = len(rec)
-            self.iters += 1
+            self.local_games += 1
+            self.iters = self.local_games
         return self.iters
 
     def run(self, is_shown=False, max_games=None):
+        first = self.iters
         try:
-            while max_games is None or self.iters < max_games:
+            while max_games is None or self.iters - first < max_games:
                 self.collect_data(is_shown=is_shown)
         except KeyboardInterrupt:
             pass
         finally:
-            self.writer.flush()
+            self.close()
         return self.iters
+
+    def close(self):
+        if self.npy is not None:
+            self.npy.flush()
+        if self.h5 is not None:
+            self.h5.close()
+            self.h5 = None
+
+
+def merge_h5_shards(shard_paths, out_path, gzip_level=4):
+    """Fold per-rank ``data.h5`` shards into one file numbered game_0.. in increasing shard index
+    order (rank-interleaved, as ``global_game_index`` assigned them)."""
+    games = []
+    for p in shard_paths:
+        with h5lite.H5Reader(p) as r:
+            for name in r.root_links():
+                games.append((int(name.split("_")[1]), p, name))
+    games.sort()
+    out = h5lite.H5ReplayWriter(out_path, gzip_level=gzip_level, flush_every=64)
+    for _, p, name in games:
+        with h5lite.H5Reader(p) as r:
+            d = r.read_group(name)
+        out.add(d["states"], d["mcts_probs"], d["winners"])
+    n = out.iters
+    out.close()
+    return n
 
 
 if __name__ == "__main__":
@@ -83,4 +125,6 @@ if __name__ == "__main__":
     parser.add_argument("--games", type=int, default=4096)
     parser.add_argument("--max-games", type=int, default=None)
     args = parser.parse_args()
-    CollectPipeline(init_model=args.model, n_games=args.games).run(is_shown=args.show, max_games=args.max_games)
+    rank, local_rank, world = distributed.shard_info()
+    CollectPipeline(init_model=args.model, n_games=args.games, rank=rank, world=world).run(
+        is_shown=args.show, max_games=args.max_games)

@@ -6,18 +6,19 @@ from chinesechesszero_b200.net import Net, BatchedEvaluator, FLOP_PER_POSITION
 
 torch.manual_seed(0)
 net = Net().cuda().eval()
-for fused in (True, False):
-    ev = BatchedEvaluator(net, fused_epilogue=fused)
-    for g in (1024, 4096, 8192):
+for bench_mode in (False, True):
+    torch.backends.cudnn.benchmark = bench_mode
+    ev = BatchedEvaluator(net, fused_epilogue=True)
+    for g in (2048, 4096, 8192):
         x = (torch.rand(g, 17, 7, 10, 9, device="cuda") > 0.9).to(torch.bfloat16)
         for _ in range(3):
             ev.forward(x)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5):
+        for _ in range(20):
             ev.forward(x)
         e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        print(json.dumps({"fused": fused, "batch": g, "ms": ms, "tflops": g * FLOP_PER_POSITION / ms / 1e9,
+        ms = e0.elapsed_time(e1) / 20
+        print(json.dumps({"cudnn_benchmark": bench_mode, "batch": g, "ms": ms, "tflops": g * FLOP_PER_POSITION / ms / 1e9,
                           "pos_per_s": g / ms * 1e3}))

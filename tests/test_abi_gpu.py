@@ -1,0 +1,92 @@
+"""C-ABI behaviour on the device: status codes and ccz_last_error for bad arguments (no crash, no
+silent fallback), the host-facing PolicyValueNet.policy_value_fn, and the device-resident move path."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cchess_shim as cs
+from oracle import net_oracle
+from tests.test_mcts_gpu import fake_evaluator
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bad_arguments_return_status_and_message():
+    from chinesechesszero_b200 import _lib
+
+    lib = _lib.load()
+    boards = _lib.boards_start(4)
+    ids = torch.empty((4, 128), dtype=torch.int16, device="cuda")
+    counts = torch.empty(4, dtype=torch.int16, device="cuda")
+    flags = torch.empty(4, dtype=torch.uint8, device="cuda")
+    s = _lib.stream_ptr()
+    assert lib.ccz_movegen_encode(boards.data_ptr(), -1, ids.data_ptr(), counts.data_ptr(), flags.data_ptr(), None, s) < 0
+    assert b"n < 0" in lib.ccz_last_error()
+    assert lib.ccz_movegen_encode(None, 4, ids.data_ptr(), counts.data_ptr(), flags.data_ptr(), None, s) < 0
+    assert b"NULL" in lib.ccz_last_error()
+    # misaligned board pointer
+    assert lib.ccz_movegen_encode(boards.data_ptr() + 1, 1, ids.data_ptr(), counts.data_ptr(), flags.data_ptr(), None, s) < 0
+    assert b"aligned" in lib.ccz_last_error()
+    # n == 0 is a no-op
+    assert lib.ccz_movegen_encode(None, 0, None, None, None, None, s) == 0
+    with pytest.raises(_lib.CczError):
+        _lib.movegen_encode(torch.zeros((2, 96), dtype=torch.uint8))  # host tensor: device pointers only
+    a = _lib.Arena(2, 64)
+    bad = _lib.ArenaStruct.from_buffer_copy(a.struct)
+    bad.d_value = None
+    assert lib.ccz_mcts_reset(ctypes.byref(bad), None, s) < 0 and b"NULL" in lib.ccz_last_error()
+    b2 = _lib.Arena(3, 64)
+    chosen = torch.zeros(2, dtype=torch.int16, device="cuda")
+    assert lib.ccz_mcts_advance(a.ref, b2.ref, chosen.data_ptr(), s) < 0 and b"geometry" in lib.ccz_last_error()
+    assert lib.ccz_mcts_advance(a.ref, a.ref, chosen.data_ptr(), s) < 0 and b"distinct" in lib.ccz_last_error()
+    assert lib.ccz_mcts_expand_backup(a.ref, chosen.data_ptr(), chosen.data_ptr(), 7, chosen.data_ptr(),
+                                      chosen.data_ptr(), chosen.data_ptr(), chosen.data_ptr(), s) < 0
+    torch.cuda.synchronize()
+
+
+def test_board_push_without_keys_and_invalid_ids():
+    from chinesechesszero_b200 import _lib
+
+    boards = _lib.boards_start(3)
+    mv = torch.tensor([cs.action_table()[0][19, 22], -1, 5000], dtype=torch.int16, device="cuda")  # b2e2, skip, skip
+    _lib.board_push(boards, mv, None)
+    out = boards.cpu().numpy()
+    ref = cs.Board()
+    ref.push(cs.Move.from_uci("b2e2"))
+    assert np.array_equal(out[0][:92], ref.record()[:92])
+    assert np.array_equal(out[1], cs.start_record()) and np.array_equal(out[2], cs.start_record())
+
+
+def test_policy_value_fn_matches_fp32_oracle():
+    from chinesechesszero_b200.net import PolicyValueNet
+
+    torch.manual_seed(0)
+    pv = PolicyValueNet(num_channels=64, resblocks_num=4)
+    net_oracle.perturb_(pv.policy_value_net.state_dict(), seed=3)
+    board = cs.Board()
+    for u in ["h2e2", "h9g7", "e2e6"]:  # cannon takes the e6 pawn with check
+        board.push(cs.Move.from_uci(u))
+    act_probs, value = pv.policy_value_fn(board.record())
+    ids, probs = zip(*act_probs)
+    id_of = cs.action_table()[0]
+    assert list(ids) == [int(id_of[m.from_square, m.to_square]) for m in board.legal_moves]
+    sd = {k: v.detach().cpu().float() for k, v in pv.policy_value_net.state_dict().items()}
+    logp, v = net_oracle.forward(sd, net_oracle.search_planes(board.record()[None]))
+    ref = np.exp(logp.numpy().reshape(-1))[list(ids)]
+    assert np.abs(np.array(probs) - ref).max() < 1e-2 and abs(float(value[0, 0]) - float(v[0, 0])) < 1e-2
+    assert value.shape == (1, 1)
+
+
+def test_resident_move_path_matches_host_path_in_deterministic_mode():
+    from chinesechesszero_b200.selfplay import SelfPlayEngine
+
+    ev = fake_evaluator("hash")
+    a = SelfPlayEngine(ev, n_games=5, n_playout=30, deterministic=True, node_cap=8192)
+    b = SelfPlayEngine(ev, n_games=5, n_playout=30, deterministic=True, node_cap=8192)
+    for _ in range(4):
+        a.play_move()
+        b.play_move_resident()
+        assert torch.equal(a.search.root_boards, b.search.root_boards)
+    assert int(b._res["finished"]) == 0 and a.total_moves == b.total_moves == 20

@@ -128,3 +128,24 @@ def test_collect_pipeline_writes_npy_triple(tmp_path):
     assert states.shape[0] == mcts.shape[0] == winners.shape[0] == meta["total_count"] == n * 5 * 2
     assert np.allclose(mcts.sum(axis=1), 1.0, atol=1e-9)
     assert (states[:, 16] == 1).all()  # reference mode: turn plane always ones
+    # the same games in the reference's data.h5 layout (collect.py:146-167)
+    from chinesechesszero_b200 import h5lite
+
+    with h5lite.H5Reader(str(tmp_path / "data.h5")) as r:
+        assert int(r.root_attrs()["iters"]) == n
+        rows = 0
+        for k in range(n):
+            d = r.read_group(f"game_{k}")
+            t2 = d["states"].shape[0]
+            assert np.array_equal(d["states"], states[rows:rows + t2])
+            assert np.array_equal(d["mcts_probs"], mcts[rows:rows + t2])
+            assert np.array_equal(d["winners"].astype(np.float32), winners[rows:rows + t2])
+            rows += t2
+        assert rows == states.shape[0]
+    # a second pipeline on the same directory continues the game counter (collect.py:39-45)
+    pipe2 = CollectPipeline(n_games=8, n_playout=6, data_dir=str(tmp_path), max_game_moves=5, node_cap=4096,
+                            net_kwargs=dict(num_channels=32, resblocks_num=2), write_npy=False)
+    assert pipe2.iters == n
+    pipe2.run(max_games=8)
+    with h5lite.H5Reader(str(tmp_path / "data.h5")) as r:
+        assert int(r.root_attrs()["iters"]) == pipe2.iters >= n + 8

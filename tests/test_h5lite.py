@@ -92,3 +92,30 @@ def test_uncompressed_and_empty(tmp_path):
     with h5lite.H5Reader(path) as r:
         d = r.read_group("game_0")
         assert np.array_equal(d["states"], s) and np.array_equal(d["winners"], z)
+
+
+def test_merge_rank_shards(tmp_path):
+    from chinesechesszero_b200 import distributed
+    from chinesechesszero_b200.collect import merge_h5_shards
+
+    rng = np.random.default_rng(5)
+    world, per_rank = 2, 3
+    truth = {}
+    paths = []
+    for rank in range(world):
+        p = str(tmp_path / f"rank{rank}" / "data.h5")
+        w = h5lite.H5ReplayWriter(p)
+        for i in range(per_rank):
+            g = _game(rng, 2)
+            k = distributed.global_game_index(i, rank, world)
+            truth[k] = g
+            w.add(*g, index=k)
+        w.close()
+        paths.append(p)
+    merged = str(tmp_path / "data.h5")
+    assert merge_h5_shards(paths, merged) == world * per_rank
+    with h5lite.H5Reader(merged) as r:
+        assert int(r.root_attrs()["iters"]) == 6
+        for k in range(6):
+            d = r.read_group(f"game_{k}")
+            assert np.array_equal(d["states"], truth[k][0]) and np.array_equal(d["mcts_probs"], truth[k][1])
