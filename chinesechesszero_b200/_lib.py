@@ -146,6 +146,7 @@ def movegen_encode(boards: torch.Tensor, planes: bool = True, out=None):
     """
     n = boards.shape[0]
     dev = boards.device
+    _ptr(boards)  # device + contiguity check before anything is allocated
     if out is None:
         move_ids = torch.empty((n, MAX_MOVES), dtype=torch.int16, device=dev)
         counts = torch.empty((n,), dtype=torch.int16, device=dev)
