@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--movegen-positions", type=int, default=1 << 20)
     ap.add_argument("--no-movegen", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[4] train-step section")
     ap.add_argument("--cpu-moves", type=int, default=1, help="moves of the CPU-port sample")
     return ap.parse_args()
 
@@ -235,6 +236,34 @@ def bench_movegen(torch, _lib, n_positions: int, peaks):
     }
 
 
+def bench_train(torch, batch: int = 512, steps: int = 5):
+    """configs[4]: the PolicyValueNet training step (train.py:130-267 semantics) in bf16, batch 512, on
+    synthetic replay rows resident on the device."""
+    from chinesechesszero_b200.train import TrainPipeline
+
+    torch.manual_seed(0)
+    pipe = TrainPipeline(batch_size=batch)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    states = (torch.rand((batch, 17, 7, 10, 9), device="cuda", generator=g) > 0.95).float()
+    pi = torch.rand((batch, 2086), device="cuda", generator=g) ** 8
+    pi = pi / pi.sum(1, keepdim=True)
+    z = torch.randint(-1, 2, (batch,), device="cuda", generator=g).float()
+    for _ in range(2):
+        pipe.train_step(states, pi, z)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for _ in range(steps):
+        last = pipe.train_step(states, pi, z)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": f"configs[4]: PolicyValueNet train step, bf16 autocast, batch {batch} (old/new policy eval, "
+                        "weight+optimizer backup, fwd/bwd, clip 5.0, Adam, KL)", "value": batch / ms * 1e3,
+            "unit": "samples/s", "ms_per_step": ms, "loss": last["loss"], "kl": last["kl"]}
+
+
 def run_own_arm(args):
     import torch
 
@@ -357,6 +386,10 @@ def run_own_arm(args):
     }
     if not args.no_movegen:
         line["movegen"] = bench_movegen(torch, _lib, args.movegen_positions, peaks)
+    if not args.no_train:
+        del eng, ev
+        torch.cuda.empty_cache()
+        line["train"] = bench_train(torch)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_moves, P)
     print(json.dumps(line))

@@ -42,6 +42,9 @@ if __name__ == "__main__":
     if what in ("game", "all"):
         from scripts import golden_game
         golden_game.main(GOLDEN)
+    if what in ("train", "all"):
+        from scripts import golden_train
+        golden_train.main(GOLDEN)
     if what in ("net", "all"):
         from scripts import golden_net
         golden_net.main(GOLDEN)
