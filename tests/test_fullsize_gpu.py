@@ -1,0 +1,90 @@
+"""BASELINE-size runs checked through size-independent properties (the oracle is too slow there):
+K1 on 1,048,576 positions (configs[1]) and the arena kernels on 4096 lockstep games (configs[2])."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_movegen_encode_one_million_positions_properties():
+    from chinesechesszero_b200 import _lib, positions
+
+    boards = positions.bench_positions(1 << 20, seed=0)
+    n = boards.shape[0]
+    assert n == 1 << 20
+    ids, counts, flags, planes = _lib.movegen_encode(boards)
+    c = counts.to(torch.int64)
+    assert int(c.min()) >= 1 and int(c.max()) <= 119
+    # ids valid, distinct and -1 padded exactly after the count
+    col = torch.arange(128, device="cuda").view(1, -1)
+    valid = col < c.view(-1, 1)
+    assert bool(((ids >= 0) == valid).all()) and int(ids.max()) < 2086
+    sorted_ids, _ = torch.sort(ids.to(torch.int32).masked_fill(~valid, 1 << 20), dim=1)
+    dup = (sorted_ids[:, 1:] == sorted_ids[:, :-1]) & (sorted_ids[:, 1:] < (1 << 20))
+    assert not bool(dup.any())
+    # every move starts on a square holding a piece of the side to move
+    from_of = torch.from_numpy(_lib.host_action_table()[1].astype(np.int64)).cuda()
+    fr = from_of[ids.clamp_min(0).to(torch.int64)]
+    code = torch.gather(boards[:, :90].to(torch.int64), 1, fr)
+    red = boards[:, 90:91] != 0
+    own = (code != 0) & (((code & 8) == 0) == red)
+    assert bool((own | ~valid).all())
+    # planes: ones exactly at the pieces (plays 7 / 15) and, for RED to move, the whole turn play
+    p = planes.view(n, 17, 630)
+    zero_plays = [i for i in range(16) if i not in (7, 15)]
+    assert float(p[:, zero_plays].float().abs().sum()) == 0.0
+    pieces = (boards[:, :90] != 0).sum(1)
+    assert bool(((p[:, 7].float().sum(1) + p[:, 15].float().sum(1)) == pieces).all())
+    turn_sum = p[:, 16].float().sum(1)
+    assert bool((turn_sum == 630.0 * boards[:, 90].float()).all())
+    assert bool(((planes == 0) | (planes == 1)).all())
+    # flags: perft-3/4 positions from the start are never drawn; NOMOVES would need count 0
+    assert int((flags & (_lib.FLAG_TIE_MASK | _lib.FLAG_NOMOVES)).sum()) == 0
+
+
+def test_lockstep_search_4096_games_tree_invariants():
+    from chinesechesszero_b200 import _lib
+    from chinesechesszero_b200.search import LockstepSearch
+
+    G, P = 4096, 64
+    torch.manual_seed(0)
+    logits = torch.randn(G, 2086, device="cuda")
+    values = torch.tanh(torch.randn(G, device="cuda") * 0.5)
+    s = LockstepSearch(G, node_cap=8192)
+    ev = lambda planes, boards: (logits, _lib.POLICY_LOGITS, values)
+    s.run(ev, P)
+    s.check_status()
+    a = s.arena
+    acts, visits, counts = s.root_visits()
+    # first search of a game: the root is expanded by playout 1, children receive P-1 visits (mcts.py:94, B.4)
+    assert bool((visits.sum(1) == P - 1).all()) and bool((counts == 44).all())
+    root = a.root.to(torch.int64) + torch.arange(G, device="cuda") * a.node_cap
+    assert bool((a.visits[root] == P).all())
+    assert bool((a.value.abs() <= 1.0 + 1e-6).all())
+    # every child run is inside the arena and points back to its parent
+    nn = a.n_nodes.to(torch.int64)
+    assert int(nn.max()) <= a.node_cap and int(nn.min()) >= 45
+    g0 = 17
+    base = g0 * a.node_cap
+    n0 = int(nn[g0])
+    fc = a.first_child[base:base + n0].cpu().numpy()
+    nc = a.n_child[base:base + n0].cpu().numpy()
+    par = a.parent[base:base + n0].cpu().numpy()
+    vis = a.visits[base:base + n0].cpu().numpy()
+    for i in np.nonzero(nc > 0)[0]:
+        kids = np.arange(fc[i], fc[i] + nc[i])
+        assert (par[kids] == i).all()
+        assert vis[i] == vis[kids].sum() + 1      # N(node) = sum N(children) + its own expansion visit
+    # advancing every game keeps exactly the chosen sub-tree
+    choice = visits.argmax(1, keepdim=True)
+    chosen = acts.gather(1, choice.long()).view(-1).contiguous()
+    kept_visits = visits.gather(1, choice.long()).view(-1)
+    s.advance(chosen)
+    b = s.arena
+    root2 = b.root.to(torch.int64) + torch.arange(G, device="cuda") * b.node_cap
+    assert bool((b.visits[root2] == kept_visits).all()) and bool((b.parent[root2] == -1).all())
+    s.run(ev, 8)
+    s.check_status()
+    _, v2, _ = s.root_visits()
+    assert bool((v2.sum(1) == torch.clamp(kept_visits - 1, min=0) + 8).all())
