@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-movegen", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[4] train-step section")
+    ap.add_argument("--graphs", action="store_true",
+                    help="replay the lockstep step from CUDA graphs (the forward is then timed in a separate loop)")
     ap.add_argument("--cpu-moves", type=int, default=1, help="moves of the CPU-port sample")
     return ap.parse_args()
 
@@ -301,8 +303,9 @@ def run_own_arm(args):
             self.pairs.append((e0, e1))
             return out
 
-    ev = TimedEvaluator()
-    eng = SelfPlayEngine(ev, n_games=G, n_playout=P, node_cap=args.node_cap, seed=D.rank_seed(1234, rank))
+    ev = base_eval if args.graphs else TimedEvaluator()
+    eng = SelfPlayEngine(ev, n_games=G, n_playout=P, node_cap=args.node_cap, seed=D.rank_seed(1234, rank),
+                         use_graphs=args.graphs)
 
     def barrier():
         D.barrier()
@@ -319,7 +322,8 @@ def run_own_arm(args):
 
     # ---- timed region 1: `value`, everything resident in HBM --------------------------------
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
-    ev.on = True
+    if not args.graphs:
+        ev.on = True
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
@@ -327,11 +331,17 @@ def run_own_arm(args):
         eng.play_move_resident()
     s1.record()
     barrier()
-    ev.on = False
+    if not args.graphs:
+        ev.on = False
     dev_ms = max_over_ranks(s0.elapsed_time(s1))
     clocks = sampler.stop() if sampler else None
-    fwd_ms = [a.elapsed_time(b) for a, b in ev.pairs]
-    ev.pairs = []
+    if args.graphs:
+        # events cannot sit inside a captured graph: attribute the whole step to the forward, which
+        # gives a lower bound on its throughput (its live share is 0.994 in the eager run)
+        fwd_ms = [s0.elapsed_time(s1) / (args.steps * P)]
+    else:
+        fwd_ms = [a.elapsed_time(b) for a, b in ev.pairs]
+        ev.pairs = []
     fwd_avg = sum(fwd_ms) / len(fwd_ms)
     n_fwd = len(fwd_ms)
     eng.search.check_status()
@@ -357,7 +367,7 @@ def run_own_arm(args):
 
     tflops = G * FLOP_PER_POSITION / fwd_avg / 1e9
     peak_tf = peaks["bf16_tflops_sustained"]
-    step_share = fwd_avg * n_fwd / s0.elapsed_time(s1)
+    step_share = None if args.graphs else fwd_avg * n_fwd / s0.elapsed_time(s1)
     line = {
         "metric": metric_name(P), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -365,7 +375,7 @@ def run_own_arm(args):
         "config": {
             "workload": f"configs[2]: lockstep batched self-play, {G} concurrent games x {P} playouts per GPU, "
                         "random-init 40x256 PolicyValueNet",
-            "games_per_gpu": G, "n_playout": P, "node_cap": args.node_cap, "parallelism": f"games sharded x{world}, "
+            "games_per_gpu": G, "n_playout": P, "node_cap": args.node_cap, "cuda_graphs": bool(args.graphs), "parallelism": f"games sharded x{world}, "
             "no collective on the hot path",
             "l2": "per-layer activations 4096x256x90 bf16 = 189 MB > 126 MB L2 (inputs larger than L2)",
             "step": "one lockstep move = n_playout x (select, movegen+encode, bf16 forward, expand+backup) + move "

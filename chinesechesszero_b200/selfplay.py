@@ -53,7 +53,7 @@ class GameRecord:
 class SelfPlayEngine:
     def __init__(self, evaluator: Callable, n_games: int, n_playout: int = 400, c_puct: float = 5.0,
                  temp: float = 1.0, node_cap: int | None = None, device="cuda", seed: int = 0,
-                 deterministic: bool = False, max_game_moves: int | None = None):
+                 deterministic: bool = False, max_game_moves: int | None = None, use_graphs: bool = False):
         self.evaluator = evaluator
         self.n_games, self.n_playout = int(n_games), int(n_playout)
         self.temp = float(temp)
@@ -63,6 +63,8 @@ class SelfPlayEngine:
             # every playout adds at most one expansion of <= 119 children; reuse keeps a sub-tree.
             node_cap = max(4096, int(self.n_playout * 64 * 2))
         self.search = LockstepSearch(n_games, node_cap=node_cap, device=device, c_puct=c_puct)
+        if use_graphs:  # replay the lockstep step from CUDA graphs (capture-safe evaluators only)
+            self.search.enable_graphs(evaluator)
         self.rng = np.random.default_rng(seed)
         self.device = self.search.device
         g = self.n_games

@@ -90,3 +90,29 @@ def test_resident_move_path_matches_host_path_in_deterministic_mode():
         b.play_move_resident()
         assert torch.equal(a.search.root_boards, b.search.root_boards)
     assert int(b._res["finished"]) == 0 and a.total_moves == b.total_moves == 20
+
+
+def test_cuda_graph_replay_equals_eager_search():
+    """The captured lockstep step (K3 -> K1 -> bf16 forward -> K4/K5) replayed from CUDA graphs gives
+    the same trees as eager launches, across an advance (second arena side, second graph)."""
+    from chinesechesszero_b200.net import BatchedEvaluator, Net
+    from chinesechesszero_b200.search import LockstepSearch
+
+    torch.manual_seed(0)
+    ev = BatchedEvaluator(Net(num_channels=32, resblocks_num=2).cuda().eval())
+    outs = []
+    for graphs in (False, True):
+        s = LockstepSearch(n_games=16, node_cap=8192)
+        if graphs:
+            s.enable_graphs(ev)
+        res = []
+        for move in range(3):
+            s.run(ev, 25)
+            s.check_status()
+            acts, visits, counts = s.root_visits()
+            res.append((acts.clone(), visits.clone(), s.arena.value[: 16 * 8192: 8192].clone()))
+            chosen = acts.gather(1, visits.argmax(1, keepdim=True).long()).view(-1).contiguous()
+            s.advance(chosen)
+        outs.append(res)
+    for (a0, v0, q0), (a1, v1, q1) in zip(*outs):
+        assert torch.equal(a0, a1) and torch.equal(v0, v1) and torch.equal(q0, q1)
