@@ -73,7 +73,11 @@ class MCTS:
         if node_cap is None:
             node_cap = max(8192, min(int(n_playout) * 128 + 256, 1 << 21))
         self._search = LockstepSearch(1, node_cap=node_cap, device=device, c_puct=float(c_puct))
-        self._fresh = True
+        from .net import BatchedEvaluator
+
+        if isinstance(self._evaluator, BatchedEvaluator):
+            # batch-1 playouts are launch-bound: replay the captured step (K3, K1, forward, K4/K5)
+            self._search.enable_graphs(self._evaluator)
 
     def _sync_root(self, board: Board) -> None:
         """Point the arena's root at ``board``; the tree is kept when the position is the one the
@@ -88,17 +92,17 @@ class MCTS:
         """mcts.py:131-166: n_playout playouts, then softmax(1/temp*log(visits+1e-10)) over the root
         children in generation order.  Returns (acts tuple, probs float64 array)."""
         self._sync_root(board)
-        interval = max(1, self.n_playout // 100)
-        acc = 0
-        for i in range(self.n_playout):
-            self._search.step(self._evaluator)
-            acc += 1
-            if on_playout is not None and (acc >= interval or i == self.n_playout - 1):
+        interval = max(1, self.n_playout // 100)  # progress throttle, mcts.py:148-160
+        remaining = self.n_playout
+        while remaining > 0:
+            chunk = min(interval, remaining) if on_playout is not None else remaining
+            self._search.run(self._evaluator, chunk)
+            remaining -= chunk
+            if on_playout is not None:
                 try:
-                    on_playout(acc)
+                    on_playout(chunk)
                 except Exception:
                     pass
-                acc = 0
         self._search.check_status()
         acts, visits, counts = self._search.root_visits()
         n = int(counts[0])

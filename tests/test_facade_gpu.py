@@ -149,3 +149,23 @@ def test_collect_pipeline_writes_npy_triple(tmp_path):
     pipe2.run(max_games=8)
     with h5lite.H5Reader(str(tmp_path / "data.h5")) as r:
         assert int(r.root_attrs()["iters"]) == pipe2.iters >= n + 8
+
+
+def test_mcts_ai_with_real_net_uses_graphs_and_reports_progress():
+    from chinesechesszero_b200.board import Board
+    from chinesechesszero_b200.mcts import MCTS_AI
+    from chinesechesszero_b200.net import PolicyValueNet
+
+    torch.manual_seed(0)
+    pv = PolicyValueNet(num_channels=32, resblocks_num=2)
+    ai = MCTS_AI(pv.policy_value_fn, c_puct=5, n_playout=200, is_selfplay=True)
+    assert ai.mcts._search._graphs is not None
+    board = Board()
+    seen = []
+    np.random.seed(0)
+    for _ in range(3):
+        move, probs = ai.get_action(board, temp=1.0, return_prob=True, on_playout=seen.append)
+        assert abs(probs.sum() - 1.0) < 1e-9 and probs[int(move)] > 0
+        assert int(move) in board.legal_ids().tolist()
+        board.push(int(move))
+    assert sum(seen) == 600 and max(seen) == 2
