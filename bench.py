@@ -272,6 +272,9 @@ def run_own_arm(args):
     from chinesechesszero_b200 import distributed as D
 
     rank, local_rank, world = D.shard_info()
+    # NCCL prints its version banner on stdout at init when NCCL_DEBUG=VERSION/INFO; stdout must carry
+    # exactly one JSON line, so keep only warnings (NCCL is used for the barrier / max-reduce only)
+    os.environ["NCCL_DEBUG"] = "WARN"
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
