@@ -272,13 +272,22 @@ def run_own_arm(args):
     from chinesechesszero_b200 import distributed as D
 
     rank, local_rank, world = D.shard_info()
-    # NCCL prints its version banner on stdout at init when NCCL_DEBUG=VERSION/INFO; stdout must carry
-    # exactly one JSON line, so keep only warnings (NCCL is used for the barrier / max-reduce only)
-    os.environ["NCCL_DEBUG"] = "WARN"
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    D.init("nccl", device=torch.device("cuda", local_rank))
+    # NCCL writes its version banner to stdout when the first communicator is created; stdout must
+    # carry exactly one JSON line, so fd 1 points at stderr while the group comes up
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        D.init("nccl", device=torch.device("cuda", local_rank))
+        D.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     from chinesechesszero_b200 import _lib
     from chinesechesszero_b200.net import FLOP_PER_POSITION, BatchedEvaluator, Net
