@@ -169,3 +169,24 @@ def test_mcts_ai_with_real_net_uses_graphs_and_reports_progress():
         assert int(move) in board.legal_ids().tolist()
         board.push(int(move))
     assert sum(seen) == 600 and max(seen) == 2
+
+
+def test_selfplay_train_loop_refreshes_the_evaluator(tmp_path):
+    from chinesechesszero_b200.loop import SelfPlayTrainLoop
+
+    torch.manual_seed(0)
+    loop = SelfPlayTrainLoop(n_games=8, n_playout=6, data_dir=str(tmp_path / "data"), model_dir=str(tmp_path / "models"),
+                             batch_size=16, games_per_iteration=8, max_game_moves=4, node_cap=4096,
+                             net_kwargs=dict(num_channels=32, resblocks_num=2))
+    ev = loop.collect.policy_value_net.evaluator()
+    w0 = ev.stem[0].clone()
+    r1 = loop.iterate()
+    assert r1["games"] >= 8 and r1["samples"] == r1["games"] * 4 * 2 and np.isfinite(r1["loss"])
+    assert not torch.equal(w0, ev.stem[0])          # trained weights were folded back into the evaluator
+    r2 = loop.iterate()
+    assert r2["games"] >= 16 and r2["samples"] > r1["samples"]
+    loop.close()
+    assert (tmp_path / "models" / "current_policy.pkl").exists() and (tmp_path / "data" / "data.h5").exists()
+    # the checkpoint is a plain state_dict with the reference's keys (net.py:208-209)
+    sd = torch.load(tmp_path / "models" / "current_policy.pkl", map_location="cpu")
+    assert "conv_block.weight" in sd and "policy_fc.bias" in sd
