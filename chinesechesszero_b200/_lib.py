@@ -71,6 +71,12 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = library_path()
+    if path == _build.OUT and _build.is_stale():
+        try:  # same image on the GPU box: nvcc is there, so a missing / outdated library is rebuilt in-tree
+            _build.build()
+        except Exception as e:  # noqa: BLE001 - reported below if the library is still missing
+            if not os.path.exists(path):
+                raise CczError(f"building {path} failed ({e}); there is no CPU fallback") from e
     if not os.path.exists(path):
         raise CczError(
             f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
