@@ -69,11 +69,12 @@ class SelfPlayEngine:
         self.device = self.search.device
         g = self.n_games
         self.move_count = np.zeros(g, dtype=np.int64)          # moves already played in each slot
-        self._boards = [[] for _ in range(g)]
-        self._acts = [[] for _ in range(g)]
-        self._probs = [[] for _ in range(g)]
-        self._turns = [[] for _ in range(g)]
-        self._moves = [[] for _ in range(g)]
+        # per-move frames of the whole batch (boards, sparse pi, turns, moves); a slot's current game is
+        # the frame range [_start[g], _n_frames)
+        self._frames: list[dict] = []
+        self._frame0 = 0
+        self._n_frames = 0
+        self._start = np.zeros(g, dtype=np.int64)
         # pinned staging for the per-move read-back / upload
         pin = dict(pin_memory=True)
         self._h_acts = torch.empty((g, _lib.MAX_MOVES), dtype=torch.int16, **pin)
@@ -99,12 +100,6 @@ class SelfPlayEngine:
         mc = self.move_count + 1
         return np.where(mc <= 30, self.temp, max(0.1, self.temp * 0.5))
 
-    def _choose(self, acts: np.ndarray, probs: np.ndarray) -> int:
-        if self.deterministic:
-            return int(acts[int(np.argmax(probs))])
-        p = (1 - EPS) * probs + EPS * self.rng.dirichlet(ALPHA * np.ones(len(probs)))
-        return int(self.rng.choice(acts, p=p / p.sum()))
-
     def play_move(self) -> list[GameRecord]:
         """One lockstep move in every slot; returns the games that finished with it."""
         s = self.search
@@ -119,26 +114,35 @@ class SelfPlayEngine:
         self.d2h_bytes += sum(t.numel() * t.element_size() for t in
                               (self._h_acts, self._h_visits, self._h_counts, self._h_boards))
         acts_np, visits_np = self._h_acts.numpy(), self._h_visits.numpy()
-        counts_np, boards_np = self._h_counts.numpy(), self._h_boards.numpy()
+        counts_np, boards_np = self._h_counts.numpy().astype(np.int64), self._h_boards.numpy()
+        if (counts_np <= 0).any():
+            raise _lib.CczError(f"game {int(np.argmin(counts_np))}: root has no children after search")
         temps = self.current_temps()
         chosen = self._h_chosen.numpy()
-        dense = np.zeros(_lib.N_ACTIONS)
-        for g in range(self.n_games):
-            n = int(counts_np[g])
-            if n <= 0:
-                raise _lib.CczError(f"game {g}: root has no children after search")
-            a = acts_np[g, :n].copy()
-            p = visit_softmax(visits_np[g, :n], float(temps[g]))
-            mv = self._choose(a, p)                             # mcts.py:216-224 (un-normalised probs)
-            dense[:] = 0.0                                      # mcts.py:212-215
-            dense[a] = p
-            p = (dense / np.sum(dense))[a]                      # game.py:187-190, same summation order
-            chosen[g] = mv
-            self._boards[g].append(boards_np[g].copy())
-            self._acts[g].append(a)
-            self._probs[g].append(p)
-            self._turns[g].append(bool(boards_np[g, 90]))
-            self._moves[g].append(mv)
+        probs_pad = np.zeros((self.n_games, _lib.MAX_MOVES), dtype=np.float64)
+        # games with the same child count and temperature are processed together; every row goes
+        # through the reference's arithmetic unchanged (element-wise ops and contiguous row sums)
+        key = counts_np * 2 + (temps != self.temp)
+        for k in np.unique(key):
+            rows = np.nonzero(key == k)[0]
+            n, t = int(counts_np[rows[0]]), float(temps[rows[0]])
+            a = acts_np[rows, :n].astype(np.int64)
+            x = 1.0 / t * np.log(visits_np[rows, :n] + 1e-10)                  # mcts.py:165
+            p = np.exp(x - np.max(x, axis=1, keepdims=True))                   # tools.py:126-129
+            p /= np.sum(p, axis=1, keepdims=True)
+            if self.deterministic:
+                pick = np.argmax(p, axis=1)
+            else:                                                              # mcts.py:216-222
+                mix = (1 - EPS) * p + EPS * self.rng.dirichlet(ALPHA * np.ones(n), size=len(rows))
+                cdf = np.cumsum(mix / np.sum(mix, axis=1, keepdims=True), axis=1)
+                pick = np.minimum((cdf < self.rng.random(len(rows))[:, None]).sum(axis=1), n - 1)
+            chosen[rows] = a[np.arange(len(rows)), pick]
+            dense = np.zeros((len(rows), _lib.N_ACTIONS))                      # mcts.py:212-215
+            dense[np.arange(len(rows))[:, None], a] = p
+            probs_pad[rows, :n] = p / np.sum(dense, axis=1, keepdims=True)     # game.py:187-190
+        self._frames.append(dict(boards=boards_np.copy(), acts=acts_np.copy(), probs=probs_pad,
+                                 counts=counts_np, turns=boards_np[:, 90] != 0, moves=chosen.copy()))
+        self._n_frames += 1
         self.move_count += 1
         self.total_moves += self.n_games
         self._d_chosen.copy_(self._h_chosen, non_blocking=True)
@@ -164,20 +168,39 @@ class SelfPlayEngine:
             self.h2d_bytes += self.n_games
             s.reset(self._d_mask)
             self.total_games += len(finished)
+            self._prune_frames()
         return finished
+
+    def _game_frames(self, g: int):
+        return self._frames[int(self._start[g]) - self._frame0: self._n_frames - self._frame0]
+
+    def current_moves(self, g: int) -> list[int]:
+        """Moves played so far in slot g's current game."""
+        return [int(f["moves"][g]) for f in self._game_frames(g)]
 
     def _finish(self, g: int, flags: int, turn_red: bool) -> GameRecord:
         winner = outcome_winner_flags(flags, turn_red) if (flags & (_lib.FLAG_TIE_MASK | _lib.FLAG_NOMOVES)) else None
-        turns = np.array(self._turns[g], dtype=bool)
+        frames = self._game_frames(g)
+        turns = np.array([bool(f["turns"][g]) for f in frames], dtype=bool)
         z = np.zeros(len(turns), dtype=np.float64)
         if winner is not None:
             z[:] = np.where(turns == winner, 1.0, -1.0)
-        rec = GameRecord(boards=np.stack(self._boards[g]), acts=self._acts[g], probs=self._probs[g], turns=turns,
-                         moves=np.array(self._moves[g], dtype=np.int16), winner=winner, z=z, final_flags=flags,
-                         slot=g)
-        self._boards[g], self._acts[g], self._probs[g], self._turns[g], self._moves[g] = [], [], [], [], []
+        counts = [int(f["counts"][g]) for f in frames]
+        rec = GameRecord(boards=np.stack([f["boards"][g] for f in frames]),
+                         acts=[f["acts"][g, :n].copy() for f, n in zip(frames, counts)],
+                         probs=[f["probs"][g, :n].copy() for f, n in zip(frames, counts)], turns=turns,
+                         moves=np.array([f["moves"][g] for f in frames], dtype=np.int16), winner=winner, z=z,
+                         final_flags=flags, slot=g)
+        self._start[g] = self._n_frames
         self.move_count[g] = 0
         return rec
+
+    def _prune_frames(self) -> None:
+        keep_from = int(self._start.min())
+        drop = keep_from - self._frame0
+        if drop > 0:
+            del self._frames[:drop]
+            self._frame0 = keep_from
 
     # ------------------------------------------------------------------------------------
     def _resident_state(self):

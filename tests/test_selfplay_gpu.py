@@ -89,6 +89,6 @@ def test_noise_mode_runs_and_is_seed_reproducible():
     for _ in range(2):
         eng = SelfPlayEngine(fake_evaluator("hash"), n_games=6, n_playout=24, seed=11, node_cap=8192)
         eng.play(3)
-        outs.append([list(m) for m in eng._moves])
+        outs.append([eng.current_moves(g) for g in range(6)])
     assert outs[0] == outs[1]
     assert len({tuple(m) for m in outs[0]}) > 1  # noise makes the slots diverge
