@@ -60,8 +60,11 @@ class SelfPlayEngine:
         self.deterministic = bool(deterministic)
         self.max_game_moves = max_game_moves
         if node_cap is None:
-            # every playout adds at most one expansion of <= 119 children; reuse keeps a sub-tree.
-            node_cap = max(4096, int(self.n_playout * 64 * 2))
+            # Per move a tree gains n_playout expansions of ~41 (at most 119) children on top of the
+            # sub-tree kept by the last advance().  With kept fraction f the steady state is about
+            # 41*n_playout/(1-f) nodes: 4x the per-move growth covers f <= 0.75 (a random-init net keeps
+            # ~1/40).  Strongly peaked nets want more (22 B/node/arena; overflow raises, never truncates).
+            node_cap = max(4096, int(self.n_playout * 41 * 4))
         self.search = LockstepSearch(n_games, node_cap=node_cap, device=device, c_puct=c_puct)
         if use_graphs:  # replay the lockstep step from CUDA graphs (capture-safe evaluators only)
             self.search.enable_graphs(evaluator)
