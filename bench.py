@@ -358,6 +358,8 @@ def run_own_arm(args):
     n_fwd = len(fwd_ms)
     eng.search.check_status()
     value = world * G * args.steps / dev_ms * 1e3
+    drained = eng.drain_resident()  # untimed: the per-move samples the resident path kept on the device
+    resident_samples = int(drained["boards"].shape[0]) * G
 
     # ---- timed region 2: `e2e`, host-facing API (D2H visit read-back, host move choice, H2D) ----
     h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
@@ -387,7 +389,8 @@ def run_own_arm(args):
         "config": {
             "workload": f"configs[2]: lockstep batched self-play, {G} concurrent games x {P} playouts per GPU, "
                         "random-init 40x256 PolicyValueNet",
-            "games_per_gpu": G, "n_playout": P, "node_cap": args.node_cap, "cuda_graphs": bool(args.graphs), "parallelism": f"games sharded x{world}, "
+            "games_per_gpu": G, "n_playout": P, "node_cap": args.node_cap, "cuda_graphs": bool(args.graphs),
+            "resident_samples_kept_on_device": resident_samples, "parallelism": f"games sharded x{world}, "
             "no collective on the hot path",
             "l2": "per-layer activations 4096x256x90 bf16 = 189 MB > 126 MB L2 (inputs larger than L2)",
             "step": "one lockstep move = n_playout x (select, movegen+encode, bf16 forward, expand+backup) + move "

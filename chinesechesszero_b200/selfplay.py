@@ -53,12 +53,14 @@ class GameRecord:
 class SelfPlayEngine:
     def __init__(self, evaluator: Callable, n_games: int, n_playout: int = 400, c_puct: float = 5.0,
                  temp: float = 1.0, node_cap: int | None = None, device="cuda", seed: int = 0,
-                 deterministic: bool = False, max_game_moves: int | None = None, use_graphs: bool = False):
+                 deterministic: bool = False, max_game_moves: int | None = None, use_graphs: bool = False,
+                 resident_ring: int = 16):
         self.evaluator = evaluator
         self.n_games, self.n_playout = int(n_games), int(n_playout)
         self.temp = float(temp)
         self.deterministic = bool(deterministic)
         self.max_game_moves = max_game_moves
+        self.resident_ring = int(resident_ring)
         if node_cap is None:
             # Per move a tree gains n_playout expansions of ~41 (at most 119) children on top of the
             # sub-tree kept by the last advance().  With kept fraction f the steady state is about
@@ -216,9 +218,17 @@ class SelfPlayEngine:
                 idx=torch.arange(_lib.MAX_MOVES, device=dev).view(1, -1),
                 move_count=torch.zeros(g, dtype=torch.int64, device=dev),
                 finished=torch.zeros((), dtype=torch.int64, device=dev),
-                last_pi=torch.zeros((g, _lib.MAX_MOVES), dtype=torch.float64, device=dev),
-                last_boards=torch.zeros((g, _lib.BOARD_BYTES), dtype=torch.uint8, device=dev),
                 chosen=torch.zeros(g, dtype=torch.int16, device=dev),
+                # device ring of per-move samples (what play_move() hands to the host every move):
+                # positions searched, root actions, un-noised pi, counts, moves played, finished mask
+                ring=self.resident_ring, head=0, filled=0,
+                ring_boards=torch.zeros((self.resident_ring, g, _lib.BOARD_BYTES), dtype=torch.uint8, device=dev),
+                ring_acts=torch.zeros((self.resident_ring, g, _lib.MAX_MOVES), dtype=torch.int16, device=dev),
+                ring_pi=torch.zeros((self.resident_ring, g, _lib.MAX_MOVES), dtype=torch.float64, device=dev),
+                ring_counts=torch.zeros((self.resident_ring, g), dtype=torch.int16, device=dev),
+                ring_moves=torch.zeros((self.resident_ring, g), dtype=torch.int16, device=dev),
+                ring_over=torch.zeros((self.resident_ring, g), dtype=torch.uint8, device=dev),
+                ring_flags=torch.zeros((self.resident_ring, g), dtype=torch.uint8, device=dev),
             )
         return self._res
 
@@ -244,8 +254,12 @@ class SelfPlayEngine:
             mix = (1 - EPS) * pi + EPS * gam / gam.sum(dim=1, keepdim=True).clamp_min(1e-300)
             choice = torch.multinomial(mix, 1, generator=r["gen"])
         r["chosen"].copy_(acts.gather(1, choice).view(g))
-        r["last_pi"].copy_(pi)
-        r["last_boards"].copy_(s.root_boards)
+        slot = r["head"]
+        r["ring_boards"][slot].copy_(s.root_boards)
+        r["ring_acts"][slot].copy_(acts)
+        r["ring_pi"][slot].copy_(pi)
+        r["ring_counts"][slot].copy_(counts)
+        r["ring_moves"][slot].copy_(r["chosen"])
         s.advance(r["chosen"])
         _lib.movegen_encode(s.root_boards, planes=False, out=self._flag_out)
         over = (self._flag_out[2] & (_lib.FLAG_TIE_MASK | _lib.FLAG_NOMOVES)) != 0
@@ -253,10 +267,27 @@ class SelfPlayEngine:
         if self.max_game_moves is not None:
             over = over | (mc >= self.max_game_moves)
         self._d_mask.copy_(over.to(torch.uint8))
+        r["ring_over"][slot].copy_(self._d_mask)
+        r["ring_flags"][slot].copy_(self._flag_out[2])
+        r["head"] = (slot + 1) % r["ring"]
+        r["filled"] = min(r["filled"] + 1, r["ring"])
         s.reset(self._d_mask)
         r["move_count"] = torch.where(over, torch.zeros_like(mc), mc)
         r["finished"] += over.sum()
         self.total_moves += g
+
+    def drain_resident(self) -> dict:
+        """Host copies of the samples of the last ``filled`` resident moves, oldest first:
+        boards (M,G,96), acts (M,G,128), pi (M,G,128) float64, counts, moves, over (slot finished with
+        that move), flags (of the position after the move).  Empties the ring."""
+        r = self._resident_state()
+        m, ring, head = r["filled"], r["ring"], r["head"]
+        order = [(head - m + i) % ring for i in range(m)]
+        idx = torch.tensor(order, dtype=torch.int64, device=self.device)
+        out = {k: r["ring_" + k].index_select(0, idx).cpu().numpy()
+               for k in ("boards", "acts", "pi", "counts", "moves", "over", "flags")}
+        r["filled"] = 0
+        return out
 
     def play(self, n_moves: int) -> list[GameRecord]:
         out = []

@@ -98,3 +98,33 @@ def outcome_winner_flags(flags, turn_red: bool):
     if fl & _lib.FLAG_NOMOVES:
         return not turn_red
     return None
+
+
+_LEVELS = {"DEBUG": 1, "INFO": 2, "WARNING": 3, "ERROR": 4, "CRITICAL": 5}
+
+
+def log(message: str, level: str = "INFO", log_path: str | None = None):
+    """Same call signature and behaviour as the reference logger (tools.py:12-71): every message is
+    appended to ``<log_path or ./logs>/<script>.log``; the console shows levels >= parameters.LOG_LEVEL."""
+    import os
+    import sys
+    import time
+
+    from . import parameters
+
+    lvl = (level or "INFO").upper()
+    rank = _LEVELS.get(lvl, 2)
+    script = os.path.splitext(os.path.basename(sys.argv[0] or "app"))[0] or "app"
+    target_dir = log_path or os.path.join(os.getcwd(), "logs")
+    try:
+        os.makedirs(target_dir, exist_ok=True)
+        with open(os.path.join(target_dir, f"{script}.log"), "a", encoding="utf-8") as f:
+            f.write(f"{time.strftime('%Y-%m-%d %H:%M:%S')} | {lvl:<8} | {message}\n")
+    except OSError:
+        pass
+    try:
+        threshold = max(1, min(5, int(parameters.LOG_LEVEL)))
+    except (TypeError, ValueError):
+        threshold = 2
+    if rank >= threshold:
+        print(f"[{lvl}] {message}", file=sys.stderr)

@@ -59,3 +59,22 @@ def test_struct_layout_matches_header():
     from chinesechesszero_b200 import _lib
 
     assert ctypes.sizeof(_lib.ArenaStruct) == 8 + 12 * 8
+
+
+def test_header_is_valid_c_and_matches_ctypes_struct(tmp_path):
+    """include/ccz_b200.h compiles as plain C (it is the drop-in boundary) and sizeof(ccz_arena)
+    equals the ctypes mirror."""
+    import subprocess
+
+    from chinesechesszero_b200 import _lib
+
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "ccz_b200.h"\n'
+                   'int main(void){printf("%zu %d %d %d\\n", sizeof(ccz_arena), CCZ_BOARD_BYTES, CCZ_N_ACTIONS, '
+                   'CCZ_FLAG_TIE_MASK);return 0;}\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(_lib.ArenaStruct)
+    assert [int(x) for x in out[1:]] == [_lib.BOARD_BYTES, _lib.N_ACTIONS, _lib.FLAG_TIE_MASK]

@@ -90,6 +90,17 @@ def test_resident_move_path_matches_host_path_in_deterministic_mode():
         b.play_move_resident()
         assert torch.equal(a.search.root_boards, b.search.root_boards)
     assert int(b._res["finished"]) == 0 and a.total_moves == b.total_moves == 20
+    # the resident path keeps every move's sample in its device ring: same data the host path recorded
+    d = b.drain_resident()
+    assert d["boards"].shape == (4, 5, 96) and d["pi"].shape == (4, 5, 128)
+    for m in range(4):
+        for g in range(5):
+            f = a._frames[m]
+            n = int(f["counts"][g])
+            assert np.array_equal(d["boards"][m, g], f["boards"][g]) and int(d["counts"][m, g]) == n
+            assert np.array_equal(d["acts"][m, g, :n], f["acts"][g, :n]) and int(d["moves"][m, g]) == int(f["moves"][g])
+            assert np.allclose(d["pi"][m, g, :n], f["probs"][g, :n], rtol=0, atol=1e-12)
+    assert not d["over"].any() and b.drain_resident()["boards"].shape[0] == 0
 
 
 def test_cuda_graph_replay_equals_eager_search():
