@@ -28,7 +28,7 @@ POLICY_PROBS, POLICY_LOGITS = 0, 1
 EXPORTS = (
     "ccz_version", "ccz_last_error", "ccz_init", "ccz_action_table", "ccz_boards_start",
     "ccz_movegen_encode", "ccz_board_keys_init", "ccz_board_push", "ccz_mcts_reset", "ccz_mcts_select",
-    "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack",
+    "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack", "ccz_conv3x3_c256",
 )
 
 
@@ -98,6 +98,7 @@ def load() -> ctypes.CDLL:
     lib.ccz_mcts_root_visits.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp, vp, vp]
     lib.ccz_mcts_advance.argtypes = [ctypes.POINTER(ArenaStruct), ctypes.POINTER(ArenaStruct), vp, vp]
     lib.ccz_replay_pack.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.ccz_conv3x3_c256.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     for name in EXPORTS:
         if name not in ("ccz_last_error",):
             getattr(lib, name).restype = i32
@@ -274,3 +275,34 @@ def replay_pack(hist_boards, turn_plane, acts, probs, counts):
             "ccz_replay_pack",
         )
     return states, pi
+
+
+def conv3x3_c256(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, skip: torch.Tensor | None = None,
+                 out: torch.Tensor | None = None, cta_group: int = 0) -> torch.Tensor:
+    """K9: relu(conv3x3_pad1(x, w) + bias [+ skip]) on the tcgen05 tensor cores.
+
+    ``x`` / ``skip`` / ``out``: bf16 ``(n,256,10,9)`` tensors in ``torch.channels_last`` memory
+    format (= NHWC rows of 256 channels); ``w``: bf16 ``(256,256,3,3)`` channels_last; ``bias`` fp32 (256,).
+    """
+    cl = torch.channels_last
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or bias.dtype != torch.float32:
+        raise CczError("conv3x3_c256: x and w must be bfloat16, bias float32")
+    if tuple(x.shape[1:]) != (256, 10, 9) or tuple(w.shape) != (256, 256, 3, 3) or bias.numel() != 256:
+        raise CczError("conv3x3_c256: shapes must be x (n,256,10,9), w (256,256,3,3), bias (256,)")
+    if not x.is_contiguous(memory_format=cl) or not w.is_contiguous(memory_format=cl):
+        raise CczError("conv3x3_c256: x and w must be channels_last")
+    if skip is not None and (skip.shape != x.shape or skip.dtype != x.dtype or not skip.is_contiguous(memory_format=cl)):
+        raise CczError("conv3x3_c256: skip must match x (bf16, channels_last)")
+    if out is None:
+        out = torch.empty_like(x, memory_format=cl)
+    elif out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous(memory_format=cl):
+        raise CczError("conv3x3_c256: out must match x (bf16, channels_last)")
+    if not (x.is_cuda and w.is_cuda and bias.is_cuda and out.is_cuda):
+        raise CczError("device tensor expected (the C ABI takes device pointers)")
+    with torch.cuda.device(x.device):
+        check(
+            load().ccz_conv3x3_c256(x.data_ptr(), w.data_ptr(), bias.data_ptr(), None if skip is None else skip.data_ptr(),
+                                    out.data_ptr(), int(x.shape[0]), int(cta_group), stream_ptr(x.device)),
+            "ccz_conv3x3_c256",
+        )
+    return out

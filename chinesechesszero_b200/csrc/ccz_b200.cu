@@ -12,6 +12,7 @@
 #include "ccz_movegen.cuh"
 #include "ccz_mcts.cuh"
 #include "ccz_replay.cuh"
+#include "ccz_conv.cuh"
 
 namespace {
 
@@ -360,6 +361,44 @@ int ccz_replay_pack(const uint8_t *d_hist_boards, const uint8_t *d_turn_plane, c
     CCZ_CUDA(cudaMemsetAsync(d_pi, 0, (size_t)2 * n * ccz::N_ACTIONS * sizeof(double), s));
     ccz::replay_pi_kernel<<<(n * 32 + threads - 1) / threads, threads, 0, s>>>(d_acts, d_probs, d_counts, n, d_pi);
     return check_launch("replay_pi_kernel");
+}
+
+int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, const void *d_skip, void *d_y, int n_boards,
+                     int cta_group, ccz_stream_t s) {
+    namespace cv = ccz::conv;
+    if (n_boards < 0) return fail(-1, "ccz_conv3x3_c256: n_boards < 0");
+    if (n_boards == 0) return 0;
+    if (!d_x || !d_w || !d_bias || !d_y) return fail(-1, "ccz_conv3x3_c256: NULL pointer");
+    if (d_y == d_x) return fail(-1, "ccz_conv3x3_c256: output must not alias the input (halo reads)");
+    if (cta_group == 0) cta_group = 2;
+    if (cta_group != 1 && cta_group != 2) return fail(-1, "ccz_conv3x3_c256: cta_group must be 0, 1 or 2");
+    if (((uintptr_t)d_x | (uintptr_t)d_w | (uintptr_t)d_y | (uintptr_t)d_skip) & 15)
+        return fail(-1, "ccz_conv3x3_c256: pointers must be 16-byte aligned");
+    static cv::Driver drv;
+    if (const char *err = cv::driver_init(drv)) return fail(-3, err);
+    const long long m = (long long)n_boards * cv::BOARD_HW;
+    const int rows_per_tile = cv::BM * cta_group;
+    const int n_tiles = (int)((m + rows_per_tile - 1) / rows_per_tile);
+    CUtensorMap tx, tw, ts, ty;
+    if (!cv::encode_im2col(drv, &tx, d_x, n_boards)) return fail(-3, "ccz_conv3x3_c256: cuTensorMapEncodeIm2col(x) failed");
+    if (!cv::encode_rows(drv, &tw, d_w, cv::BN, 9 * cv::C, (uint32_t)(cv::BN / cta_group)))
+        return fail(-3, "ccz_conv3x3_c256: cuTensorMapEncodeTiled(w) failed");
+    if (!cv::encode_rows(drv, &ty, d_y, (uint64_t)m, cv::C, cv::BM)) return fail(-3, "ccz_conv3x3_c256: cuTensorMapEncodeTiled(y) failed");
+    if (d_skip) {
+        if (!cv::encode_rows(drv, &ts, d_skip, (uint64_t)m, cv::C, cv::BM))
+            return fail(-3, "ccz_conv3x3_c256: cuTensorMapEncodeTiled(skip) failed");
+    } else {
+        ts = ty;
+    }
+    cudaError_t e;
+    if (cta_group == 2)
+        e = d_skip ? cv::launch_variant<2, true>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, s)
+                   : cv::launch_variant<2, false>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, s);
+    else
+        e = d_skip ? cv::launch_variant<1, true>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, s)
+                   : cv::launch_variant<1, false>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, s);
+    if (e != cudaSuccess) return fail(-2, "conv3x3_c256_kernel launch", e);
+    return 0;
 }
 
 } // extern "C"

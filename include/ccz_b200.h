@@ -143,6 +143,15 @@ int ccz_replay_pack(const uint8_t *d_hist_boards /*[n,8,96]: history slots, most
                     const double *d_probs /*[n,128]*/, const int16_t *d_counts, int n,
                     void *d_states_f16 /*[2n,10710]*/, double *d_pi /*[2n,2086]*/, ccz_stream_t s);
 
+/* K9: the residual-tower convolution of Net.forward (net.py:33-41, 82-90) with eval-mode BatchNorm folded
+ * in: y = relu(conv3x3_pad1(x, w) + bias [+ skip]) over n_boards boards of 10x9, 256 -> 256 channels.
+ * d_x, d_skip, d_y: [n_boards,10,9,256] bf16 (NHWC = torch channels_last); d_w: [256][3][3][256] bf16
+ * (out, kh, kw, in = a channels_last [256,256,3,3] weight); d_bias: fp32[256]; d_skip NULL = no skip
+ * connection (conv1 of a block), d_skip may alias d_y but d_y must not alias d_x.  tcgen05 implicit GEMM
+ * with TMA im2col loads; cta_group 0 = default (2: CTA pairs on 256x256 tiles), 1 = single-CTA tiles. */
+int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, const void *d_skip, void *d_y,
+                     int n_boards, int cta_group, ccz_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif
