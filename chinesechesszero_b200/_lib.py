@@ -297,6 +297,8 @@ def conv3x3_c256(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, skip: tor
         out = torch.empty_like(x, memory_format=cl)
     elif out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous(memory_format=cl):
         raise CczError("conv3x3_c256: out must match x (bf16, channels_last)")
+    if cta_group not in (0, 1, 2):
+        raise CczError("conv3x3_c256: cta_group must be 0 (default), 1 or 2")
     if not (x.is_cuda and w.is_cuda and bias.is_cuda and out.is_cuda):
         raise CczError("device tensor expected (the C ABI takes device pointers)")
     with torch.cuda.device(x.device):

@@ -11,6 +11,8 @@ back in fp32; the softmax over all 2086 actions is fused into the expand kernel'
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -93,10 +95,27 @@ class BatchedEvaluator:
     which is the evaluator protocol of :class:`search.LockstepSearch`.
     """
 
-    def __init__(self, net: Net, device="cuda", dtype=torch.bfloat16, fused_epilogue: bool = True):
+    #: which kernel runs the 3x3 tower convolutions:
+    #:   "k9"      hand-written tcgen05 / TMA-im2col kernel (csrc/ccz_conv.cuh) for every 256->256 conv
+    #:   "k9_skip" K9 for the conv that ends a residual block (bias + skip + ReLU epilogue), cuDNN's fused
+    #:             conv+bias+ReLU for the first conv of the block
+    #:   "cudnn"   cuDNN's fused epilogues for both
+    #:   "torch"   unfused F.conv2d (CPU-capable; used by the fp32 folding test)
+    CONV_IMPLS = ("k9", "k9_skip", "cudnn", "torch")
+
+    def __init__(self, net: Net, device="cuda", dtype=torch.bfloat16, fused_epilogue: bool = True,
+                 conv_impl: str | None = None):
         self.device = torch.device(device)
         self.dtype = dtype
-        self.fused = fused_epilogue
+        if conv_impl is None:
+            conv_impl = os.environ.get("CCZ_CONV_IMPL", "k9_skip") if fused_epilogue else "torch"
+        if conv_impl not in self.CONV_IMPLS:
+            raise ValueError(f"conv_impl must be one of {self.CONV_IMPLS}")
+        k9_ok = self.device.type == "cuda" and dtype == torch.bfloat16 and net.conv_block.out_channels == 256
+        if conv_impl in ("k9", "k9_skip") and not k9_ok:
+            conv_impl = "cudnn"  # K9 is specialised for the 256-channel bf16 tower of the reference net
+        self.conv_impl = conv_impl
+        self.fused = conv_impl != "torch"
         self.n_evals = 0
         self.refresh(net)
 
@@ -108,7 +127,7 @@ class BatchedEvaluator:
 
         def conv_params(conv, bn):
             w, b = _fold(conv, bn)
-            return w.to(dev, dt).contiguous(memory_format=cl), b.to(dev, dt)
+            return w.to(dev, dt).contiguous(memory_format=cl), b.to(dev, dt), b.to(dev, torch.float32).contiguous()
 
         self.stem = conv_params(net.conv_block, net.conv_block_bn)
         self.blocks = [(conv_params(rb.conv1, rb.conv1_bn), conv_params(rb.conv2, rb.conv2_bn))
@@ -123,14 +142,18 @@ class BatchedEvaluator:
         self.value_fc2 = (net.value_fc2.weight.detach().to(dev, torch.float32),
                           net.value_fc2.bias.detach().to(dev, torch.float32))
 
-    def _conv_relu(self, x, wb):
-        w, b = wb
+    def _conv_relu(self, x, wb, k9=False):
+        w, b, b32 = wb
+        if k9:
+            return _lib.conv3x3_c256(x, w, b32)
         if self.fused:
             return torch.cudnn_convolution_relu(x, w, b, (1, 1), (1, 1), (1, 1), 1)
         return F.relu_(F.conv2d(x, w, b, padding=1))
 
-    def _conv_add_relu(self, x, wb, skip):
-        w, b = wb
+    def _conv_add_relu(self, x, wb, skip, k9=False):
+        w, b, b32 = wb
+        if k9:  # the block's output overwrites its input (each tile reads its skip rows before storing them)
+            return _lib.conv3x3_c256(x, w, b32, skip=skip, out=skip)
         if self.fused:
             return torch.cudnn_convolution_add_relu(x, w, skip, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
         return F.relu_(F.conv2d(x, w, b, padding=1).add_(skip))
@@ -140,9 +163,10 @@ class BatchedEvaluator:
         g = planes.shape[0]
         x = planes.view(g, PLAYS * PIECES, 10, 9).contiguous(memory_format=torch.channels_last)
         x = self._conv_relu(x, self.stem)
+        k9_plain, k9_skip = self.conv_impl == "k9", self.conv_impl in ("k9", "k9_skip")
         for c1, c2 in self.blocks:
-            y = self._conv_relu(x, c1)
-            x = self._conv_add_relu(y, c2, x)
+            y = self._conv_relu(x, c1, k9_plain)
+            x = self._conv_add_relu(y, c2, x, k9_skip)
         h = F.relu_(F.conv2d(x, self.heads_w, self.heads_b))  # (g, 24, 10, 9)
         hp = h[:, :PLAYS].reshape(g, PLAYS * 90)               # NCHW flatten order, net.py:97
         hv = h[:, PLAYS:].reshape(g, PIECES * 90)

@@ -1,0 +1,28 @@
+"""Whole-forward time of the 40x256 evaluator per conv implementation (steady state, one GPU)."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from chinesechesszero_b200.net import Net, BatchedEvaluator, FLOP_PER_POSITION
+
+G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+impls = sys.argv[2:] or ["cudnn", "k9_skip", "k9"]
+torch.manual_seed(0)
+net = Net().cuda().eval()
+planes = (torch.rand(G, 17, 7, 10, 9, device="cuda") > 0.9).to(torch.bfloat16)
+ref = None
+for impl in impls:
+    ev = BatchedEvaluator(net, conv_impl=impl)
+    for _ in range(3):
+        logits, v = ev.forward(planes)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ev.forward(planes)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    p = torch.softmax(logits, 1)
+    if ref is None:
+        ref = (p, v)
+    print(json.dumps({"conv_impl": impl, "batch": G, "ms": ms, "tflops": G * FLOP_PER_POSITION / ms / 1e9, "moves_per_s_at_400": 1e3 * G / (400 * ms),
+                      "max_dp_vs_first": (p - ref[0]).abs().max().item(), "max_dv_vs_first": (v - ref[1]).abs().max().item()}), flush=True)

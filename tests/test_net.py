@@ -64,13 +64,14 @@ def test_bn_folding_is_exact_in_fp32_on_cpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["seed0", "perturbed"])
-@pytest.mark.parametrize("fused", [True, False])
-def test_bf16_evaluator_within_tolerance(gold, name, fused):
+@pytest.mark.parametrize("conv_impl", ["k9", "k9_skip", "cudnn", "torch"])
+def test_bf16_evaluator_within_tolerance(gold, name, conv_impl):
     from chinesechesszero_b200 import _lib
     from chinesechesszero_b200.net import BatchedEvaluator
 
     net = _product_net(name == "perturbed").cuda()
-    ev = BatchedEvaluator(net, fused_epilogue=fused)
+    ev = BatchedEvaluator(net, conv_impl=conv_impl)
+    assert ev.conv_impl == conv_impl  # the 256-channel product net takes the hand-written tcgen05 path
     boards = torch.from_numpy(gold["records"]).cuda()
     _, _, _, planes = _lib.movegen_encode(boards)
     logits, v = ev.forward(planes)
