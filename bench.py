@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--graphs", action="store_true",
                     help="replay the lockstep step from CUDA graphs (the forward is then timed in a separate loop)")
     ap.add_argument("--cpu-moves", type=int, default=1, help="moves of the CPU-port sample")
+    ap.add_argument("--conv-impl", default=None, choices=["k9", "k9_skip", "cudnn"],
+                    help="tower convolution kernel (default: the evaluator's default, K9 = csrc/ccz_conv.cuh)")
+    ap.add_argument("--conv-sample", type=int, default=8, help="bracket every K9 launch of every n-th forward with CUDA events")
     return ap.parse_args()
 
 
@@ -296,22 +299,26 @@ def run_own_arm(args):
     peaks = measured_peaks()
     torch.manual_seed(0)  # same random-init weights on every rank (net.py:120 default init)
     net = Net().cuda().eval()
-    base_eval = BatchedEvaluator(net)
+    base_eval = BatchedEvaluator(net, conv_impl=args.conv_impl)
     G, P = args.games, args.playouts
 
     # per-phase device timing of the lockstep step: events around the forward and around our kernels
     class TimedEvaluator:
         def __init__(self):
             self.pairs = []
+            self.conv = []  # (with_skip, start, end) of every K9 launch of the sampled forwards
             self.on = False
 
         def __call__(self, planes, leaf_boards):
             if not self.on:
                 return base_eval(planes, leaf_boards)
+            sample = args.conv_sample > 0 and len(self.pairs) % args.conv_sample == 0
+            base_eval.conv_events = self.conv if sample else None
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = base_eval(planes, leaf_boards)
             e1.record()
+            base_eval.conv_events = None
             self.pairs.append((e0, e1))
             return out
 
@@ -353,7 +360,8 @@ def run_own_arm(args):
         fwd_ms = [s0.elapsed_time(s1) / (args.steps * P)]
     else:
         fwd_ms = [a.elapsed_time(b) for a, b in ev.pairs]
-        ev.pairs = []
+        conv_ms = [(sk, a.elapsed_time(b)) for sk, a, b in ev.conv]
+        ev.pairs, ev.conv = [], []
     fwd_avg = sum(fwd_ms) / len(fwd_ms)
     n_fwd = len(fwd_ms)
     eng.search.check_status()
@@ -382,6 +390,32 @@ def run_own_arm(args):
     tflops = G * FLOP_PER_POSITION / fwd_avg / 1e9
     peak_tf = peaks["bf16_tflops_sustained"]
     step_share = None if args.graphs else fwd_avg * n_fwd / s0.elapsed_time(s1)
+    forward = {"kernel": f"bf16 Net.forward over the leaf batch (conv_impl={base_eval.conv_impl}: 3x3 tower on "
+                         + ("K9 ccz::conv3x3_c256_kernel" if base_eval.conv_impl.startswith("k9") else "cuDNN")
+                         + ", stem / 1x1 heads / FC through cuDNN + cuBLAS)",
+               "achieved": tflops, "unit": "TFLOP/s", "frac": tflops / peak_tf, "flop_per_launch": G * FLOP_PER_POSITION,
+               "ms_per_launch": fwd_avg, "launches_timed": n_fwd, "share_of_step": step_share}
+    conv_flop = 2.0 * G * 90 * 256 * 2304  # one 3x3 256->256 convolution over G boards
+    if not args.graphs and conv_ms:
+        # dominant kernel = K9: mean duration of the launches bracketed inside the timed region
+        k_avg = sum(t for _, t in conv_ms) / len(conv_ms)
+        k_plain = [t for sk, t in conv_ms if not sk]
+        k_skip = [t for sk, t in conv_ms if sk]
+        per_fwd = len(conv_ms) / max(1, (n_fwd + args.conv_sample - 1) // args.conv_sample)
+        roof = {"bound": "tensor", "achieved": conv_flop / k_avg / 1e9, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": conv_flop / k_avg / 1e9 / peak_tf, "traffic": ncu_traffic("conv3x3_c256_kernel", G),
+                "kernel": "ccz::conv3x3_c256_kernel (K9: tcgen05 implicit GEMM, TMA im2col, bias+skip+ReLU epilogue)",
+                "flop_per_launch": conv_flop, "ms_per_launch": k_avg, "launches_timed": len(conv_ms),
+                "launches_per_forward": per_fwd,
+                "ms_plain": sum(k_plain) / len(k_plain) if k_plain else None,
+                "ms_with_skip": sum(k_skip) / len(k_skip) if k_skip else None,
+                "share_of_step": k_avg * per_fwd * n_fwd / s0.elapsed_time(s1),
+                "peak_source": peaks["source"] + " sustained", "forward": forward}
+    else:
+        roof = {"bound": "tensor", "achieved": tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": tflops / peak_tf,
+                "traffic": None, "peak_source": peaks["source"] + " sustained", **{k: v for k, v in forward.items()
+                                                                                   if k not in ("achieved", "unit", "frac")}}
+    k9_per_fwd = {"k9": 80, "k9_skip": 40}.get(base_eval.conv_impl, 0)
     line = {
         "metric": metric_name(P), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -400,12 +434,8 @@ def run_own_arm(args):
                 "ms_per_step": e2e_ms / args.steps,
                 "api": "SelfPlayEngine.play_move(): per-move visit counts / boards / flags read back to pinned host "
                        "memory, host-side visit softmax + seeded Dirichlet choice, chosen moves uploaded"},
-        "gpu_launches": args.steps * (P * 3 + 4),
-        "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": tflops / peak_tf, "traffic": None,
-                     "kernel": "bf16 Net.forward over the leaf batch (cuDNN fused conv+bias(+skip)+ReLU, library)",
-                     "flop_per_launch": G * FLOP_PER_POSITION, "ms_per_launch": fwd_avg, "launches_timed": n_fwd,
-                     "share_of_step": step_share, "peak_source": peaks["source"] + " sustained"},
+        "gpu_launches": args.steps * (P * (3 + k9_per_fwd) + 4),
+        "roofline": roof,
         "clocks": clocks,
         "evals_per_move": P,
     }

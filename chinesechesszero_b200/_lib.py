@@ -24,6 +24,7 @@ FLAG_CHECK, FLAG_NOMOVES, FLAG_INSUFFICIENT, FLAG_FOURFOLD, FLAG_SIXTY = 1, 2, 4
 FLAG_TIE_MASK = FLAG_INSUFFICIENT | FLAG_FOURFOLD | FLAG_SIXTY
 STATUS_NODE_OVERFLOW = 1
 POLICY_PROBS, POLICY_LOGITS = 0, 1
+CONV_VARIANT_1CTA, CONV_VARIANT_PAIR, CONV_VARIANT_2PAIRS, CONV_VARIANT_4PAIRS = 1, 2, 2 | 32, 2 | 64
 
 EXPORTS = (
     "ccz_version", "ccz_last_error", "ccz_init", "ccz_action_table", "ccz_boards_start",
@@ -278,11 +279,13 @@ def replay_pack(hist_boards, turn_plane, acts, probs, counts):
 
 
 def conv3x3_c256(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, skip: torch.Tensor | None = None,
-                 out: torch.Tensor | None = None, cta_group: int = 0) -> torch.Tensor:
+                 out: torch.Tensor | None = None, variant: int = 0) -> torch.Tensor:
     """K9: relu(conv3x3_pad1(x, w) + bias [+ skip]) on the tcgen05 tensor cores.
 
     ``x`` / ``skip`` / ``out``: bf16 ``(n,256,10,9)`` tensors in ``torch.channels_last`` memory
     format (= NHWC rows of 256 channels); ``w``: bf16 ``(256,256,3,3)`` channels_last; ``bias`` fp32 (256,).
+    ``variant`` 0 = the library default; other values select the tiling for measurements
+    (``CONV_VARIANT_*``: 1 single-CTA tiles, 2 CTA pairs, 34 / 66 clusters of 2 / 4 pairs sharing weight stages).
     """
     cl = torch.channels_last
     if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or bias.dtype != torch.float32:
@@ -297,14 +300,14 @@ def conv3x3_c256(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, skip: tor
         out = torch.empty_like(x, memory_format=cl)
     elif out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous(memory_format=cl):
         raise CczError("conv3x3_c256: out must match x (bf16, channels_last)")
-    if cta_group not in (0, 1, 2):
-        raise CczError("conv3x3_c256: cta_group must be 0 (default), 1 or 2")
+    if not 0 <= variant < 128:
+        raise CczError("conv3x3_c256: variant out of range (see ccz_conv3x3_c256 in include/ccz_b200.h)")
     if not (x.is_cuda and w.is_cuda and bias.is_cuda and out.is_cuda):
         raise CczError("device tensor expected (the C ABI takes device pointers)")
     with torch.cuda.device(x.device):
         check(
             load().ccz_conv3x3_c256(x.data_ptr(), w.data_ptr(), bias.data_ptr(), None if skip is None else skip.data_ptr(),
-                                    out.data_ptr(), int(x.shape[0]), int(cta_group), stream_ptr(x.device)),
+                                    out.data_ptr(), int(x.shape[0]), int(variant), stream_ptr(x.device)),
             "ccz_conv3x3_c256",
         )
     return out

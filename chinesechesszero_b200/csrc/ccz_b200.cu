@@ -14,6 +14,10 @@
 #include "ccz_replay.cuh"
 #include "ccz_conv.cuh"
 
+#ifndef CCZ_CONV_DEFAULT_PAIRS
+#define CCZ_CONV_DEFAULT_PAIRS 1
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -364,24 +368,32 @@ int ccz_replay_pack(const uint8_t *d_hist_boards, const uint8_t *d_turn_plane, c
 }
 
 int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, const void *d_skip, void *d_y, int n_boards,
-                     int cta_group, ccz_stream_t s) {
+                     int variant, ccz_stream_t s) {
     namespace cv = ccz::conv;
     if (n_boards < 0) return fail(-1, "ccz_conv3x3_c256: n_boards < 0");
     if (n_boards == 0) return 0;
     if (!d_x || !d_w || !d_bias || !d_y) return fail(-1, "ccz_conv3x3_c256: NULL pointer");
     if (d_y == d_x) return fail(-1, "ccz_conv3x3_c256: output must not alias the input (halo reads)");
+    if (variant < 0 || variant >= 128) return fail(-1, "ccz_conv3x3_c256: bad variant");
+    // variant: 0 = default.  bits 0-1 CTA group (1 / 2), bit 2 = no tail split, bits 3-4 = traffic experiment
+    // (skips loads, WRONG results), bits 5-6 = log2(CTA pairs per cluster sharing a weight stage)
+    int cta_group = variant & 3;
+    const int tail_split = !(variant & 4), dbg = (variant >> 3) & 3;
+    int pairs = 1 << ((variant >> 5) & 3);
+    if (variant == 0) { cta_group = 2; pairs = CCZ_CONV_DEFAULT_PAIRS; }
     if (cta_group == 0) cta_group = 2;
-    if (cta_group != 1 && cta_group != 2) return fail(-1, "ccz_conv3x3_c256: cta_group must be 0, 1 or 2");
+    if (cta_group == 3 || pairs > 4 || (cta_group == 1 && pairs != 1))
+        return fail(-1, "ccz_conv3x3_c256: unsupported variant (cta_group 1|2, pairs 1|2|4, pairs > 1 needs cta_group 2)");
     if (((uintptr_t)d_x | (uintptr_t)d_w | (uintptr_t)d_y | (uintptr_t)d_skip) & 15)
         return fail(-1, "ccz_conv3x3_c256: pointers must be 16-byte aligned");
     static cv::Driver drv;
     if (const char *err = cv::driver_init(drv)) return fail(-3, err);
     const long long m = (long long)n_boards * cv::BOARD_HW;
-    const int rows_per_tile = cv::BM * cta_group;
+    const int rows_per_tile = cv::BM * cta_group * pairs;
     const int n_tiles = (int)((m + rows_per_tile - 1) / rows_per_tile);
     CUtensorMap tx, tw, ts, ty;
     if (!cv::encode_im2col(drv, &tx, d_x, n_boards)) return fail(-3, "ccz_conv3x3_c256: cuTensorMapEncodeIm2col(x) failed");
-    if (!cv::encode_rows(drv, &tw, d_w, cv::BN, 9 * cv::C, (uint32_t)(cv::BN / cta_group)))
+    if (!cv::encode_rows(drv, &tw, d_w, cv::BN, 9 * cv::C, (uint32_t)(cv::BN / cta_group / pairs)))
         return fail(-3, "ccz_conv3x3_c256: cuTensorMapEncodeTiled(w) failed");
     if (!cv::encode_rows(drv, &ty, d_y, (uint64_t)m, cv::C, cv::BM)) return fail(-3, "ccz_conv3x3_c256: cuTensorMapEncodeTiled(y) failed");
     if (d_skip) {
@@ -391,12 +403,14 @@ int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, cons
         ts = ty;
     }
     cudaError_t e;
-    if (cta_group == 2)
-        e = d_skip ? cv::launch_variant<2, true>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, s)
-                   : cv::launch_variant<2, false>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, s);
-    else
-        e = d_skip ? cv::launch_variant<1, true>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, s)
-                   : cv::launch_variant<1, false>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, s);
+#define CCZ_CONV_LAUNCH(CG, PAIRS)                                                                                      \
+    (d_skip ? cv::launch_variant<CG, PAIRS, true>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, tail_split, dbg, s)     \
+            : cv::launch_variant<CG, PAIRS, false>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, tail_split, dbg, s))
+    if (cta_group == 1) e = CCZ_CONV_LAUNCH(1, 1);
+    else if (pairs == 1) e = CCZ_CONV_LAUNCH(2, 1);
+    else if (pairs == 2) e = CCZ_CONV_LAUNCH(2, 2);
+    else e = CCZ_CONV_LAUNCH(2, 4);
+#undef CCZ_CONV_LAUNCH
     if (e != cudaSuccess) return fail(-2, "conv3x3_c256_kernel launch", e);
     return 0;
 }

@@ -191,14 +191,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 }
 // arrive on `bar` (same offset in every CTA of the pair) once all MMAs issued so far have completed
 template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint16_t cta_mask) {
     if constexpr (CG == 1) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     } else {
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                     "h"((uint16_t)3)
+                     "h"(cta_mask)
                      : "memory");
     }
+}
+// 2-D tiled load multicast to the CTAs in `cta_mask` (same smem offset in each); every destination's pair
+// leader gets the complete_tx on its copy of the barrier (`bar` = the issuer's pair-leader barrier address).
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1, "
+        "{%4, %5}], [%2], %3, %6;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1), "l"(L2_HINT_DEFAULT)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -235,13 +244,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-// grid = n_clusters * CG CTAs (persistent); cluster c handles tiles c, c + n_clusters, ...; a tile is
-// CG * 128 consecutive output pixels x all 256 output channels.
-template <int CG, bool HAS_SKIP>
+// grid = n_clusters * CG CTAs (persistent); cluster c handles work items c, c + n_clusters, ...  The first
+// n_full items are whole tiles (CG * 128 consecutive output pixels x all 256 output channels); the tiles of
+// the last, partial round are split into `split` (1, 2 or 4) channel slices of 256/split so that the tail
+// keeps every cluster busy for 1/split of a tile time instead of a few clusters for a whole one.
+struct WorkItem {
+    int tile, n_off, n_w;
+};
+__device__ __forceinline__ WorkItem work_item(int i, int n_full, int split_log2) {
+    if (i < n_full) return {i, 0, BN};
+    const int j = i - n_full, n_w = BN >> split_log2;
+    return {n_full + (j >> split_log2), (j & ((1 << split_log2) - 1)) * n_w, n_w};
+}
+
+// PAIRS > 1 (CG == 2 only): a cluster of PAIRS CTA pairs works on PAIRS consecutive tiles with the SAME weight
+// stage: each CTA fetches 1/PAIRS of its half of the weight tile and multicasts it to the CTAs of equal
+// parity, so weight traffic from L2 drops by PAIRS.  A stage is then free only when every pair has consumed it.
+template <int CG, int PAIRS, bool HAS_SKIP>
 __global__ void __launch_bounds__(THREADS, 1)
 conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                     const __grid_constant__ CUtensorMap tm_skip, const __grid_constant__ CUtensorMap tm_y, const float *__restrict__ bias,
-                    int n_tiles) {
+                    int n_items, int n_full, int split_log2, int dbg) {
     using K = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -260,8 +283,11 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     uint8_t *const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw)); // generic pointer to smem_base
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
-    const int cluster_id = blockIdx.x / CG, n_clusters = gridDim.x / CG;
+    static_assert(CG == 2 || PAIRS == 1, "weight multicast needs CTA pairs");
+    constexpr int CLUSTER = CG * PAIRS;
+    const uint32_t rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
+    const uint32_t prank = rank % CG, pair_id = rank / CG, lead_rank = rank - prank; // position in the pair / pair in the cluster
+    const int cluster_id = blockIdx.x / CLUSTER, n_clusters = gridDim.x / CLUSTER;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x);
@@ -272,7 +298,7 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < K::STAGES; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, PAIRS);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
@@ -289,38 +315,51 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         reinterpret_cast<float *>(smem_gen + (bias_smem - smem_base))[t + 128] = bias[t + 128];
     }
     tc_fence_before();
-    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if constexpr (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
 
     if (warp == 0) {
         // ===== A/B producer =====
         if (lane == 0) {
-            const uint32_t full0 = CG == 2 ? mapa(bar_full, 0) : bar_full; // the leader's full barriers
+            const uint32_t full0 = CG == 2 ? mapa(bar_full, lead_rank) : bar_full; // the pair leader's full barriers
+            constexpr int SLICE_ROWS = K::B_ROWS / PAIRS;
+            uint16_t mc_mask = 0;
+            for (int j = 0; j < PAIRS; ++j) mc_mask |= (uint16_t)(1u << (j * CG + prank));
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-                const int m0 = (tile * CG + (int)rank) * BM;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const WorkItem wi = work_item(item, n_full, split_log2);
+                const int m0 = ((wi.tile * PAIRS + (int)pair_id) * CG + (int)prank) * BM;
+                const int b_row = wi.n_off + (int)prank * (wi.n_w / CG); // a channel slice over-reads rows it does not use
                 const int img = m0 / BOARD_HW, rem = m0 - img * BOARD_HW;
                 const int p = rem / BOARD_W, q = rem - p * BOARD_W;
                 for (int kb = 0; kb < KBLOCKS; ++kb) {
                     const int tap = kb >> 2, c0 = (kb & 3) * BK;
                     const int r = tap / 3, s = tap - 3 * r;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, CG * K::STAGE_BYTES);
-                    tma_load_im2col<CG>(a_smem + stage * K::A_BYTES, &tm_x, full0 + 8 * stage, c0, q - 1, p - 1, img, (uint16_t)s, (uint16_t)r);
-                    tma_load_2d<CG>(b_smem + stage * K::B_BYTES, &tm_w, full0 + 8 * stage, kb * BK, (int)rank * K::B_ROWS);
+                    const bool do_a = !((dbg & 2) && (kb & 1)), do_b = !((dbg & 1) && (kb & 1)); // traffic-sensitivity experiment
+                    if (prank == 0) mbar_expect_tx(bar_full + 8 * stage, CG * ((do_a ? K::A_BYTES : 0) + (do_b ? K::B_BYTES : 0)));
+                    if (do_a) tma_load_im2col<CG>(a_smem + stage * K::A_BYTES, &tm_x, full0 + 8 * stage, c0, q - 1, p - 1, img, (uint16_t)s, (uint16_t)r);
+                    if constexpr (PAIRS == 1) {
+                        if (do_b) tma_load_2d<CG>(b_smem + stage * K::B_BYTES, &tm_w, full0 + 8 * stage, kb * BK, b_row);
+                    } else {
+                        tma_load_2d_mc(b_smem + stage * K::B_BYTES + (int)pair_id * SLICE_ROWS * 128, &tm_w, full0 + 8 * stage, kb * BK,
+                                       b_row + (int)pair_id * SLICE_ROWS, mc_mask);
+                    }
                     if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only) =====
-        if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(BM * CG, BN);
+        if (prank == 0 && lane == 0) {
+            constexpr uint16_t mask_cluster = (uint16_t)((1u << CLUSTER) - 1);
+            const uint16_t mask_pair = (uint16_t)(((1u << CG) - 1) << lead_rank);
             int stage = 0;
             uint32_t phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const uint32_t idesc = umma_idesc(BM * CG, work_item(item, n_full, split_log2).n_w);
                 mbar_wait_cluster(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -332,10 +371,10 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) // +32 bytes along K inside the swizzle row
                         umma_bf16<CG>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-                    umma_commit<CG>(bar_empty + 8 * stage);
+                    umma_commit<CG>(bar_empty + 8 * stage, mask_cluster);
                     if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit<CG>(bar_tfull + 8 * acc);
+                umma_commit<CG>(bar_tfull + 8 * acc, mask_pair);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -343,29 +382,30 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         // ===== skip-tile producer: prefetch skip[m0 : m0+128, :] into the staging tile =====
         if (HAS_SKIP && lane == 0) {
             uint32_t it = 0;
-            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
-                const int m0 = (tile * CG + (int)rank) * BM;
+            for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
+                const WorkItem wi = work_item(item, n_full, split_log2);
+                const int m0 = ((wi.tile * PAIRS + (int)pair_id) * CG + (int)prank) * BM;
                 mbar_wait(bar_stfree, (it & 1) ^ 1);
-                mbar_expect_tx(bar_skip, K::STAGING_BYTES);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) tma_load_2d<1>(staging + g * (BM * 128), &tm_skip, bar_skip, g * 64, m0);
+                mbar_expect_tx(bar_skip, (wi.n_w / 64) * (BM * 128));
+                for (int g = 0; g < wi.n_w / 64; ++g) tma_load_2d<1>(staging + g * (BM * 128), &tm_skip, bar_skip, wi.n_off + g * 64, m0);
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread = one output pixel (TMEM lane), 256 channels =====
         const int quarter = warp - 4, row = quarter * 32 + lane;
-        const uint32_t tempty0 = CG == 2 ? mapa(bar_tempty, 0) : bar_tempty;
+        const uint32_t tempty0 = CG == 2 ? mapa(bar_tempty, lead_rank) : bar_tempty;
         const float *bias_s = reinterpret_cast<const float *>(smem_gen + (bias_smem - smem_base));
         uint8_t *stg = smem_gen + (staging - smem_base);
         uint32_t acc = 0, acc_phase = 0, it = 0;
-        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++it) {
-            const int m0 = (tile * CG + (int)rank) * BM;
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
+            const WorkItem wi = work_item(item, n_full, split_log2);
+            const int m0 = ((wi.tile * PAIRS + (int)pair_id) * CG + (int)prank) * BM;
             if (HAS_SKIP) mbar_wait(bar_skip, it & 1);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int chunk = 0; chunk < 8; ++chunk) { // 32 channels per chunk
+            for (int chunk = 0; chunk < wi.n_w / 32; ++chunk) { // 32 channels per chunk
                 uint32_t v[32];
                 tmem_ld32(t_row + chunk * 32, v);
                 tmem_ld_wait();
@@ -374,8 +414,8 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 for (int j = 0; j < 4; ++j) {
                     const int c16 = (chunk & 1) * 4 + j; // 16-byte column of the 128-byte row
                     uint4 *cell = reinterpret_cast<uint4 *>(box_row + ((c16 ^ (row & 7)) << 4));
-                    const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + chunk * 32 + j * 8);
-                    const float4 b1 = *reinterpret_cast<const float4 *>(bias_s + chunk * 32 + j * 8 + 4);
+                    const float4 b0 = *reinterpret_cast<const float4 *>(bias_s + wi.n_off + chunk * 32 + j * 8);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(bias_s + wi.n_off + chunk * 32 + j * 8 + 4);
                     float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
                                   __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
                                   __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
@@ -408,8 +448,7 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             fence_proxy_async();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (threadIdx.x == 128) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) tma_store_2d(&tm_y, staging + g * (BM * 128), g * 64, m0);
+                for (int g = 0; g < wi.n_w / 64; ++g) tma_store_2d(&tm_y, staging + g * (BM * 128), wi.n_off + g * 64, m0);
                 tma_store_commit();
                 tma_store_wait_read();
                 if (HAS_SKIP) mbar_arrive(bar_stfree);
@@ -422,7 +461,7 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     // teardown (re-converge the single-lane role warps before the aligned barriers)
     __syncwarp();
     tc_fence_before();
-    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if constexpr (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, 512);
@@ -484,31 +523,46 @@ inline bool encode_im2col(const Driver &d, CUtensorMap *m, const void *ptr, int 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CG, bool HAS_SKIP>
+template <int CG, int PAIRS, bool HAS_SKIP>
 inline cudaError_t launch_variant(const CUtensorMap &tx, const CUtensorMap &tw, const CUtensorMap &ts, const CUtensorMap &ty, const float *bias,
-                                  int n_tiles, int n_sm, cudaStream_t stream) {
-    auto kern = conv3x3_c256_kernel<CG, HAS_SKIP>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    int clusters = n_sm / CG;
-    if (clusters > n_tiles) clusters = n_tiles;
+                                  int n_tiles, int n_sm, int tail_split, int dbg, cudaStream_t stream) {
+    auto kern = conv3x3_c256_kernel<CG, PAIRS, HAS_SKIP>;
+    constexpr int CLUSTER = CG * PAIRS;
+    static int max_clusters = 0; // resident clusters of this shape (GPC boundaries can strand SMs for CLUSTER > 2)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * CG));
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = Cfg<CG>::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CG;
+    at[0].val.clusterDim.x = CLUSTER;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, tx, tw, ts, ty, bias, n_tiles);
+    if (!max_clusters) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        cfg.gridDim = dim3((unsigned)(n_sm / CLUSTER * CLUSTER));
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        if (n < 1) return cudaErrorInvalidConfiguration;
+        max_clusters = n < n_sm / CLUSTER ? n : n_sm / CLUSTER;
+    }
+    int clusters = max_clusters;
+    // tail split: the last round has `rem` tiles for `clusters` clusters; slice them by output channels
+    // while every slice still gets its own cluster
+    const int rem = n_tiles % clusters;
+    int split_log2 = 0;
+    if (tail_split && rem > 0) {
+        while (split_log2 < 2 && (rem << (split_log2 + 1)) <= clusters) ++split_log2;
+    }
+    const int n_full = split_log2 ? n_tiles - rem : n_tiles;
+    const int n_items = n_full + (split_log2 ? rem << split_log2 : 0);
+    if (clusters > n_items) clusters = n_items;
+    cfg.gridDim = dim3((unsigned)(clusters * CLUSTER));
+    return cudaLaunchKernelEx(&cfg, kern, tx, tw, ts, ty, bias, n_items, n_full, split_log2, dbg);
 }
 
 } // namespace conv

@@ -104,11 +104,14 @@ class BatchedEvaluator:
     CONV_IMPLS = ("k9", "k9_skip", "cudnn", "torch")
 
     def __init__(self, net: Net, device="cuda", dtype=torch.bfloat16, fused_epilogue: bool = True,
-                 conv_impl: str | None = None):
+                 conv_impl: str | None = None, chunk: int | None = None):
         self.device = torch.device(device)
         self.dtype = dtype
+        # leaves per sub-batch (0 = whole batch at once): sub-batches whose activations fit the 126 MB L2
+        # keep the tower's layer-to-layer traffic out of HBM
+        self.chunk = int(os.environ.get("CCZ_EVAL_CHUNK", "0")) if chunk is None else int(chunk)
         if conv_impl is None:
-            conv_impl = os.environ.get("CCZ_CONV_IMPL", "k9_skip") if fused_epilogue else "torch"
+            conv_impl = os.environ.get("CCZ_CONV_IMPL", "k9") if fused_epilogue else "torch"
         if conv_impl not in self.CONV_IMPLS:
             raise ValueError(f"conv_impl must be one of {self.CONV_IMPLS}")
         k9_ok = self.device.type == "cuda" and dtype == torch.bfloat16 and net.conv_block.out_channels == 256
@@ -117,6 +120,9 @@ class BatchedEvaluator:
         self.conv_impl = conv_impl
         self.fused = conv_impl != "torch"
         self.n_evals = 0
+        # measurement hook (bench.py): when a list, every K9 launch of the next forwards is bracketed by CUDA
+        # events on the launching stream and the (with_skip, start, end) triples are appended to it
+        self.conv_events: list | None = None
         self.refresh(net)
 
     @torch.no_grad()
@@ -142,10 +148,20 @@ class BatchedEvaluator:
         self.value_fc2 = (net.value_fc2.weight.detach().to(dev, torch.float32),
                           net.value_fc2.bias.detach().to(dev, torch.float32))
 
+    def _k9(self, x, w, b32, skip, out):
+        if self.conv_events is None:
+            return _lib.conv3x3_c256(x, w, b32, skip=skip, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = _lib.conv3x3_c256(x, w, b32, skip=skip, out=out)
+        e1.record()
+        self.conv_events.append((skip is not None, e0, e1))
+        return y
+
     def _conv_relu(self, x, wb, k9=False):
         w, b, b32 = wb
         if k9:
-            return _lib.conv3x3_c256(x, w, b32)
+            return self._k9(x, w, b32, None, None)
         if self.fused:
             return torch.cudnn_convolution_relu(x, w, b, (1, 1), (1, 1), (1, 1), 1)
         return F.relu_(F.conv2d(x, w, b, padding=1))
@@ -153,13 +169,20 @@ class BatchedEvaluator:
     def _conv_add_relu(self, x, wb, skip, k9=False):
         w, b, b32 = wb
         if k9:  # the block's output overwrites its input (each tile reads its skip rows before storing them)
-            return _lib.conv3x3_c256(x, w, b32, skip=skip, out=skip)
+            return self._k9(x, w, b32, skip, skip)
         if self.fused:
             return torch.cudnn_convolution_add_relu(x, w, skip, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
         return F.relu_(F.conv2d(x, w, b, padding=1).add_(skip))
 
     @torch.no_grad()
     def forward(self, planes: torch.Tensor):
+        g = planes.shape[0]
+        if self.chunk and g > self.chunk:
+            parts = [self._forward(planes[i:i + self.chunk]) for i in range(0, g, self.chunk)]
+            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+        return self._forward(planes)
+
+    def _forward(self, planes: torch.Tensor):
         g = planes.shape[0]
         x = planes.view(g, PLAYS * PIECES, 10, 9).contiguous(memory_format=torch.channels_last)
         x = self._conv_relu(x, self.stem)

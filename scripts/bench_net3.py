@@ -11,18 +11,27 @@ net = Net().cuda().eval()
 planes = (torch.rand(G, 17, 7, 10, 9, device="cuda") > 0.9).to(torch.bfloat16)
 ref = None
 for impl in impls:
-    ev = BatchedEvaluator(net, conv_impl=impl)
+    impl, _, chunk = impl.partition(":")
+    ev = BatchedEvaluator(net, conv_impl=impl, chunk=int(chunk or 0))
     for _ in range(3):
         logits, v = ev.forward(planes)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run = lambda: ev.forward(planes)
+    if os.environ.get("GRAPH"):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            logits, v = ev.forward(planes)
+        run = gr.replay
+        for _ in range(10):
+            run()
     e0.record()
-    for _ in range(20):
-        ev.forward(planes)
+    for _ in range(30):
+        run()
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
+    ms = e0.elapsed_time(e1) / 30
     p = torch.softmax(logits, 1)
     if ref is None:
         ref = (p, v)
-    print(json.dumps({"conv_impl": impl, "batch": G, "ms": ms, "tflops": G * FLOP_PER_POSITION / ms / 1e9, "moves_per_s_at_400": 1e3 * G / (400 * ms),
+    print(json.dumps({"conv_impl": impl, "chunk": ev.chunk, "batch": G, "ms": ms, "tflops": G * FLOP_PER_POSITION / ms / 1e9, "moves_per_s_at_400": 1e3 * G / (400 * ms),
                       "max_dp_vs_first": (p - ref[0]).abs().max().item(), "max_dv_vs_first": (v - ref[1]).abs().max().item()}), flush=True)

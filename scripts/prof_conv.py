@@ -19,7 +19,7 @@ for _ in range(reps):
     torch.cudnn_convolution_relu(x, w, bb, (1, 1), (1, 1), (1, 1), 1)
     torch.cudnn_convolution_add_relu(x, w, skip, 1.0, bb, (1, 1), (1, 1), (1, 1), 1)
     for cg in cgs:
-        _lib.conv3x3_c256(x, w, bias, None, out=out, cta_group=cg)
-        _lib.conv3x3_c256(x, w, bias, skip, out=out, cta_group=cg)
+        _lib.conv3x3_c256(x, w, bias, None, out=out, variant=cg)
+        _lib.conv3x3_c256(x, w, bias, skip, out=out, variant=cg)
 torch.cuda.synchronize()
 print("ok")

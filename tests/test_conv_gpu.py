@@ -27,14 +27,14 @@ def _ref(x, w, bias, skip):
 
 
 @pytest.mark.parametrize("n", [1, 3, 37, 128, 300])  # ragged tails: n*90 is rarely a multiple of 128 / 256
-@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 34, 66])  # default, 1-CTA tiles, CTA pairs, 2 / 4 pairs per cluster
 @pytest.mark.parametrize("with_skip", [False, True])
-def test_conv_matches_fp32_reference(n, cta_group, with_skip):
+def test_conv_matches_fp32_reference(n, variant, with_skip):
     from chinesechesszero_b200 import _lib
 
     x, skip, w, bias = _case(n, seed=n)
     sk = skip if with_skip else None
-    y = _lib.conv3x3_c256(x, w, bias, sk, cta_group=cta_group)
+    y = _lib.conv3x3_c256(x, w, bias, sk, variant=variant)
     ref = _ref(x, w, bias, sk)
     tol = 2.0 ** -8 * ref.abs().max().item() + 1e-3
     assert (y.float() - ref).abs().max().item() <= tol
@@ -78,4 +78,4 @@ def test_conv_rejects_bad_arguments():
     with pytest.raises(_lib.CczError):
         _lib.conv3x3_c256(x, w, bias, out=x)  # output aliasing the input would corrupt halo reads
     with pytest.raises(_lib.CczError):
-        _lib.conv3x3_c256(x, w, bias, cta_group=3)
+        _lib.conv3x3_c256(x, w, bias, variant=3)
