@@ -308,6 +308,7 @@ def run_own_arm(args):
             self.pairs = []
             self.conv = []  # (with_skip, start, end) of every K9 launch of the sampled forwards
             self.on = False
+            self.needs_planes = base_eval.needs_planes  # False: the stem runs from the board records (K10)
 
         def __call__(self, planes, leaf_boards):
             if not self.on:

@@ -29,7 +29,7 @@ CONV_VARIANT_1CTA, CONV_VARIANT_PAIR, CONV_VARIANT_2PAIRS, CONV_VARIANT_4PAIRS =
 EXPORTS = (
     "ccz_version", "ccz_last_error", "ccz_init", "ccz_action_table", "ccz_boards_start",
     "ccz_movegen_encode", "ccz_board_keys_init", "ccz_board_push", "ccz_mcts_reset", "ccz_mcts_select",
-    "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack", "ccz_conv3x3_c256",
+    "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack", "ccz_conv3x3_c256", "ccz_stem_lookup",
 )
 
 
@@ -100,6 +100,7 @@ def load() -> ctypes.CDLL:
     lib.ccz_mcts_advance.argtypes = [ctypes.POINTER(ArenaStruct), ctypes.POINTER(ArenaStruct), vp, vp]
     lib.ccz_replay_pack.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.ccz_conv3x3_c256.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.ccz_stem_lookup.argtypes = [vp, i32, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("ccz_last_error",):
             getattr(lib, name).restype = i32
@@ -310,4 +311,24 @@ def conv3x3_c256(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, skip: tor
                                     out.data_ptr(), int(x.shape[0]), int(variant), stream_ptr(x.device)),
             "ccz_conv3x3_c256",
         )
+    return out
+
+
+def stem_lookup(boards: torch.Tensor, table: torch.Tensor, bias_turn: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """K10: stem conv + BN + ReLU of search-time inputs straight from ``boards`` (n,96) uint8 ->
+    bf16 ``(n,256,10,9)`` channels_last.  ``table`` bf16 (9,16,256), ``bias_turn`` fp32 (2,9,256)
+    (built by ``net.stem_tables``)."""
+    n = boards.shape[0]
+    if boards.dtype != torch.uint8 or boards.shape[1:] != (BOARD_BYTES,):
+        raise CczError("stem_lookup: boards must be uint8 (n,96)")
+    if table.dtype != torch.bfloat16 or tuple(table.shape) != (9, 16, 256) or bias_turn.dtype != torch.float32 \
+            or tuple(bias_turn.shape) != (2, 9, 256):
+        raise CczError("stem_lookup: table must be bf16 (9,16,256) and bias_turn fp32 (2,9,256)")
+    if out is None:
+        out = torch.empty((n, 256, 10, 9), dtype=torch.bfloat16, device=boards.device).contiguous(memory_format=torch.channels_last)
+    elif tuple(out.shape) != (n, 256, 10, 9) or out.dtype != torch.bfloat16 or not out.is_contiguous(memory_format=torch.channels_last):
+        raise CczError("stem_lookup: out must be bf16 (n,256,10,9) channels_last")
+    with torch.cuda.device(boards.device):
+        check(load().ccz_stem_lookup(_ptr(boards), n, _ptr(table), _ptr(bias_turn), out.data_ptr(), stream_ptr(boards.device)),
+              "ccz_stem_lookup")
     return out

@@ -13,6 +13,7 @@
 #include "ccz_mcts.cuh"
 #include "ccz_replay.cuh"
 #include "ccz_conv.cuh"
+#include "ccz_stem.cuh"
 
 #ifndef CCZ_CONV_DEFAULT_PAIRS
 #define CCZ_CONV_DEFAULT_PAIRS 1
@@ -413,6 +414,29 @@ int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, cons
 #undef CCZ_CONV_LAUNCH
     if (e != cudaSuccess) return fail(-2, "conv3x3_c256_kernel launch", e);
     return 0;
+}
+
+int ccz_stem_lookup(const uint8_t *d_boards, int n, const void *d_table, const float *d_bias_turn, void *d_y, ccz_stream_t s) {
+    namespace st = ccz::stem;
+    if (n < 0) return fail(-1, "ccz_stem_lookup: n < 0");
+    if (n == 0) return 0;
+    if (!d_boards || !d_table || !d_bias_turn || !d_y) return fail(-1, "ccz_stem_lookup: NULL pointer");
+    if (((uintptr_t)d_boards & 3) || (((uintptr_t)d_table | (uintptr_t)d_bias_turn | (uintptr_t)d_y) & 15))
+        return fail(-1, "ccz_stem_lookup: pointers must be 16-byte aligned (boards 4-byte)");
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        CCZ_CUDA(cudaGetDevice(&dev));
+        CCZ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        CCZ_CUDA(cudaFuncSetAttribute(st::stem_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::SMEM_BYTES));
+    }
+    int blocks = 2 * n_sm; // two resident CTAs (92 KB of tables each) per SM
+    const int need = (n + st::WARPS - 1) / st::WARPS;
+    if (blocks > need) blocks = need;
+    st::stem_lookup_kernel<<<blocks, st::WARPS * 32, st::SMEM_BYTES, s>>>(d_boards, n, static_cast<const uint4 *>(d_table),
+                                                                         reinterpret_cast<const float4 *>(d_bias_turn),
+                                                                         static_cast<uint4 *>(d_y));
+    return check_launch("stem_lookup_kernel");
 }
 
 } // extern "C"

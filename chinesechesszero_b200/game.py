@@ -5,8 +5,9 @@ loop line by line -- temperature schedule (game.py:159), ``get_action`` (game.py
 renormalisation (game.py:187-190), sample recording and history update BEFORE the push
 (game.py:196-201), terminal test (game.py:208), z (game.py:213-219) -- and returns the same list of
 ``(red_states, black_states, mcts_prob, winner_z)`` tuples, including the reference's aliasing of the
-two history lists across all samples (game.py:234-237).  Visualisation
-(``graphic``, ``start_play``) is out of scope.
+two history lists across all samples (game.py:234-237).
+``Game.start_play(player1, player0, is_shown=False)`` is the two-player loop of game.py:77-130
+(the batched form is ``evaluate.EvaluationMatch``).  Board drawing (``graphic``) is out of scope.
 """
 from __future__ import annotations
 
@@ -36,6 +37,25 @@ class Game:
         self.red_states.insert(0, red)
         self.black_states.pop()
         self.black_states.insert(0, black)
+
+    def start_play(self, player1, player0, is_shown=False, max_moves=None):
+        """game.py:77-130: player1 = RED moves first; returns the winner (True = RED, False = BLACK) or -1
+        for a draw.  Like the reference, only ``board.is_game_over()`` ends the game."""
+        self.board = Board(device=self.board.device)
+        player1.set_player_idx(1)
+        player0.set_player_idx(0)
+        players = {RED: player1, (not RED): player0}
+        n = 0
+        while True:
+            move = players[self.board.turn].get_action(self.board)
+            self.update_states_history()
+            self.board.push(int(move))
+            n += 1
+            if self.board.is_game_over():
+                outcome = self.board.outcome()
+                return outcome.winner if outcome.winner is not None else -1
+            if max_moves is not None and n >= max_moves:
+                return -1
 
     def start_self_play(self, player, is_shown=False, temp=1.0, game_index=None, max_moves=None):
         self.board = Board(device=self.board.device)

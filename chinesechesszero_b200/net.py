@@ -88,6 +88,28 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
     return w * scale.view(-1, 1, 1, 1), (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
 
 
+def stem_tables(w: torch.Tensor, b: torch.Tensor):
+    """Lookup tables of K10 (csrc/ccz_stem.cuh) from the folded stem weights ``w`` (256,119,3,3) -- already
+    rounded to the evaluator's dtype -- and the fp32 bias ``b``: ``table[tap][code][co]`` bf16 (9,16,256) and
+    ``bias_turn[turn][border class][co]`` fp32 (2,9,256).  Search-time inputs (net.py:160-177) are one-hot:
+    red type t -> channel 7*7 + t-1, black -> 15*7 + t-1, the turn plane is channels 16*7..16*7+6."""
+    wf = w.float()
+    co = wf.shape[0]
+    table = torch.zeros((9, 16, co), dtype=torch.float32, device=w.device)
+    for t in range(1, 8):
+        table[:, t, :] = wf[:, 7 * PIECES + t - 1].reshape(co, 9).t()
+        table[:, 8 + t, :] = wf[:, 15 * PIECES + t - 1].reshape(co, 9).t()
+    turn_w = wf[:, 16 * PIECES:17 * PIECES].sum(1)  # (co,3,3)
+    bias_turn = torch.zeros((2, 9, co), dtype=torch.float32, device=w.device)
+    for rc in range(3):
+        for cc in range(3):
+            rows = [r for r in range(3) if not (rc == 0 and r == 0) and not (rc == 2 and r == 2)]
+            cols = [c for c in range(3) if not (cc == 0 and c == 0) and not (cc == 2 and c == 2)]
+            bias_turn[0, rc * 3 + cc] = b.float()
+            bias_turn[1, rc * 3 + cc] = b.float() + turn_w[:, rows][:, :, cols].sum((1, 2))
+    return table.to(torch.bfloat16).contiguous(), bias_turn.contiguous()
+
+
 class BatchedEvaluator:
     """bf16 lockstep-batch forward of a :class:`Net` (Net.forward, net.py:82-110).
 
@@ -136,6 +158,8 @@ class BatchedEvaluator:
             return w.to(dev, dt).contiguous(memory_format=cl), b.to(dev, dt), b.to(dev, torch.float32).contiguous()
 
         self.stem = conv_params(net.conv_block, net.conv_block_bn)
+        # K10: with the tower on K9 the stem of search-time inputs is a table lookup over the board records
+        self.stem_lookup = stem_tables(self.stem[0], self.stem[2]) if self.conv_impl in ("k9", "k9_skip") else None
         self.blocks = [(conv_params(rb.conv1, rb.conv1_bn), conv_params(rb.conv2, rb.conv2_bn))
                        for rb in net.res_blocks]
         # both 1x1 heads in one convolution: 17 policy + 7 value channels
@@ -174,18 +198,32 @@ class BatchedEvaluator:
             return torch.cudnn_convolution_add_relu(x, w, skip, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
         return F.relu_(F.conv2d(x, w, b, padding=1).add_(skip))
 
-    @torch.no_grad()
-    def forward(self, planes: torch.Tensor):
-        g = planes.shape[0]
-        if self.chunk and g > self.chunk:
-            parts = [self._forward(planes[i:i + self.chunk]) for i in range(0, g, self.chunk)]
-            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
-        return self._forward(planes)
+    @property
+    def needs_planes(self) -> bool:
+        """False when ``__call__`` evaluates the stem from the board records (K10) and ignores ``planes``."""
+        return self.stem_lookup is None
 
-    def _forward(self, planes: torch.Tensor):
-        g = planes.shape[0]
-        x = planes.view(g, PLAYS * PIECES, 10, 9).contiguous(memory_format=torch.channels_last)
-        x = self._conv_relu(x, self.stem)
+    @torch.no_grad()
+    def forward(self, planes: torch.Tensor | None, boards: torch.Tensor | None = None):
+        """(logits fp32 (g,2086), values fp32 (g,)).  ``planes``: any (g,17,7,10,9) net input.  ``boards``:
+        (g,96) board records of SEARCH-TIME positions (no history planes, net.py:160-177); when given and the
+        tower runs on K9, the stem is evaluated from them by K10 and ``planes`` is not read."""
+        use_boards = boards is not None and self.stem_lookup is not None
+        g = boards.shape[0] if use_boards else planes.shape[0]
+        if self.chunk and g > self.chunk:
+            parts = [self._forward(None if use_boards else planes[i:i + self.chunk],
+                                   boards[i:i + self.chunk] if use_boards else None) for i in range(0, g, self.chunk)]
+            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+        return self._forward(None if use_boards else planes, boards if use_boards else None)
+
+    def _forward(self, planes, boards=None):
+        if boards is not None:
+            g = boards.shape[0]
+            x = _lib.stem_lookup(boards, *self.stem_lookup)
+        else:
+            g = planes.shape[0]
+            x = planes.view(g, PLAYS * PIECES, 10, 9).contiguous(memory_format=torch.channels_last)
+            x = self._conv_relu(x, self.stem)
         k9_plain, k9_skip = self.conv_impl == "k9", self.conv_impl in ("k9", "k9_skip")
         for c1, c2 in self.blocks:
             y = self._conv_relu(x, c1, k9_plain)
@@ -199,8 +237,8 @@ class BatchedEvaluator:
         return logits, v
 
     def __call__(self, planes, leaf_boards=None):
-        logits, v = self.forward(planes)
-        self.n_evals += planes.shape[0]
+        logits, v = self.forward(planes, leaf_boards)
+        self.n_evals += logits.shape[0]
         return logits, _lib.POLICY_LOGITS, v
 
 

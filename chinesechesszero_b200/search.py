@@ -7,7 +7,8 @@ no virtual loss, so each tree goes through the same sequence of states as the re
 sequential playouts.
 
 An *evaluator* is any callable ``evaluator(planes, leaf_boards) -> (policy, policy_kind, values)``
-with ``planes`` the bf16 (G,17,7,10,9) net input, ``leaf_boards`` the (G,96) uint8 records,
+with ``planes`` the bf16 (G,17,7,10,9) net input (``None`` when the evaluator has an attribute
+``needs_planes == False``), ``leaf_boards`` the (G,96) uint8 records,
 ``policy`` float32 (G,2086) (probabilities or logits, see ``_lib.POLICY_*``) and ``values``
 float32 (G,), all device tensors.
 """
@@ -71,11 +72,11 @@ class LockstepSearch:
         a.root_keys.copy_(_lib.board_keys_init(a.root_boards))
 
     # ------------------------------------------------------------------------------------
-    def select_and_encode(self) -> None:
+    def select_and_encode(self, planes: bool = True) -> None:
         a = self.arena
         _lib.mcts_select(a, self.c_puct, self.leaf_boards, self.leaf_nodes)
-        _lib.movegen_encode(self.leaf_boards, planes=True,
-                            out=(self.move_ids, self.counts, self.flags, self.planes))
+        _lib.movegen_encode(self.leaf_boards, planes=planes,
+                            out=(self.move_ids, self.counts, self.flags, self.planes if planes else None))
 
     def expand_backup(self, policy: torch.Tensor, policy_kind: int, values: torch.Tensor) -> None:
         _lib.mcts_expand_backup(self.arena, self.leaf_nodes, policy, policy_kind, values, self.move_ids,
@@ -83,8 +84,10 @@ class LockstepSearch:
 
     def step(self, evaluator) -> None:
         """One playout in every game (MCTS.playout, mcts.py:101-129)."""
-        self.select_and_encode()
-        policy, kind, values = evaluator(self.planes, self.leaf_boards)
+        # an evaluator that works from the board records (net.BatchedEvaluator with K10) spares K1 the planes
+        need = getattr(evaluator, "needs_planes", True)
+        self.select_and_encode(planes=need)
+        policy, kind, values = evaluator(self.planes if need else None, self.leaf_boards)
         self.expand_backup(policy, kind, values)
 
     def run(self, evaluator, n_playout: int) -> None:

@@ -155,6 +155,18 @@ int ccz_replay_pack(const uint8_t *d_hist_boards /*[n,8,96]: history slots, most
 int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, const void *d_skip, void *d_y,
                      int n_boards, int variant, ccz_stream_t s);
 
+/* K10: the stem convolution of Net.forward (conv_block 119->256 + BN + ReLU, net.py:84) for SEARCH-TIME
+ * inputs, computed from the board records themselves.  policy_value_fn (net.py:160-177) feeds 7 zero
+ * history states + the current one-hot piece planes + a constant turn plane, so each output pixel is
+ * bias + at most nine rows of the folded weight tensor:
+ *   d_table     bf16 [9 taps][16 piece codes][256]: W[co, channel(code), tap] (codes 0 and 8: zero rows;
+ *               code = type | 8*black -> channel 49+type-1 (red) or 105+type-1 (black); tap = kh*3+kw)
+ *   d_bias_turn fp32 [2 turn][9 border classes][256]: bias + turn * (sum of the 7 turn-plane weights over the
+ *               taps that stay on the board; class = 3*(h==0?0:h==9?2:1) + (w==0?0:w==8?2:1))
+ *   d_y         bf16 [n,10,9,256] NHWC, what ccz_conv3x3_c256 consumes. */
+int ccz_stem_lookup(const uint8_t *d_boards, int n, const void *d_table, const float *d_bias_turn, void *d_y,
+                    ccz_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,20 +8,24 @@ G = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 impls = sys.argv[2:] or ["cudnn", "k9_skip", "k9"]
 torch.manual_seed(0)
 net = Net().cuda().eval()
-planes = (torch.rand(G, 17, 7, 10, 9, device="cuda") > 0.9).to(torch.bfloat16)
+from chinesechesszero_b200 import _lib
+boards = torch.empty(G, 96, dtype=torch.uint8, device="cuda")
+_lib.check(_lib.load().ccz_boards_start(boards.data_ptr(), G, _lib.stream_ptr()), "boards_start")
+planes = _lib.movegen_encode(boards)[3]
+USE_BOARDS = bool(os.environ.get("BOARDS"))
 ref = None
 for impl in impls:
     impl, _, chunk = impl.partition(":")
     ev = BatchedEvaluator(net, conv_impl=impl, chunk=int(chunk or 0))
     for _ in range(3):
-        logits, v = ev.forward(planes)
+        logits, v = ev.forward(planes, boards if USE_BOARDS else None)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    run = lambda: ev.forward(planes)
+    run = lambda: ev.forward(planes, boards if USE_BOARDS else None)
     if os.environ.get("GRAPH"):
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
-            logits, v = ev.forward(planes)
+            logits, v = ev.forward(planes, boards if USE_BOARDS else None)
         run = gr.replay
         for _ in range(10):
             run()
