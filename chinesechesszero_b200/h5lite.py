@@ -307,6 +307,13 @@ class H5Reader:
         off = 8 if version == 1 else 4
         return tuple(struct.unpack_from("<Q", data, off + 8 * i)[0] for i in range(rank))
 
+    def dataset_shape(self, header_addr: int) -> tuple:
+        """Shape of a dataset from its data-space message, without reading the data."""
+        for mtype, data in self.messages(header_addr):
+            if mtype == 0x0001:
+                return self._parse_dataspace(data)
+        raise ValueError("object has no data-space message")
+
     def attrs(self, header_addr: int) -> dict:
         out = {}
         for mtype, data in self.messages(header_addr):

@@ -119,3 +119,38 @@ def test_merge_rank_shards(tmp_path):
         for k in range(6):
             d = r.read_group(f"game_{k}")
             assert np.array_equal(d["states"], truth[k][0]) and np.array_equal(d["mcts_probs"], truth[k][1])
+
+
+def test_convert_h5_to_npy_matches_the_reference_layout(tmp_path):
+    """convert.py:21-105: data.h5 -> states.npy / mcts.npy / winners.npy / meta.json (winners float32), games in
+    index order, a missing game index skipped."""
+    import json
+
+    from chinesechesszero_b200 import h5lite
+    from chinesechesszero_b200.convert import convert_h5_to_npy
+
+    rng = np.random.default_rng(0)
+    games = []
+    path = str(tmp_path / "data.h5")
+    w = h5lite.H5ReplayWriter(path, gzip_level=4)
+    for t in (3, 1, 5):
+        st = (rng.random((2 * t, 17, 7, 10, 9)) > 0.9).astype(np.float16)
+        pi = rng.random((2 * t, 2086))
+        z = rng.choice([-1.0, 0.0, 1.0], size=2 * t)
+        w.add(st, pi, z)
+        games.append((st, pi, z))
+    w.close()
+    out = str(tmp_path / "npy")
+    n = convert_h5_to_npy(path, out)
+    assert n == 18
+    states, mcts, winners = (np.load(f"{out}/{k}.npy") for k in ("states", "mcts", "winners"))
+    assert states.dtype == np.float16 and mcts.dtype == np.float64 and winners.dtype == np.float32
+    assert np.array_equal(states, np.concatenate([g[0] for g in games]))
+    assert np.array_equal(mcts, np.concatenate([g[1] for g in games]))
+    assert np.array_equal(winners, np.concatenate([g[2] for g in games]).astype(np.float32))
+    meta = json.load(open(f"{out}/meta.json"))
+    assert meta["total_count"] == 18 and meta["states_shape"] == [18, 17, 7, 10, 9] and meta["winners_dtype"] == "float32"
+    # what train.py:95-100 does with the result
+    from chinesechesszero_b200.train import NpyReplayDataset
+
+    assert len(NpyReplayDataset(out)) == 18
