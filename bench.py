@@ -422,7 +422,8 @@ def run_own_arm(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic (random-init net, torch.manual_seed(0); games from the start position)",
         "config": {
-            "workload": f"configs[2]: lockstep batched self-play, {G} concurrent games x {P} playouts per GPU, "
+            "workload": ("configs[3] (per-GPU shard of the 8xB200 run)" if (G, P) == (8192, 800) else "configs[2]")
+                        + f": lockstep batched self-play, {G} concurrent games x {P} playouts per GPU, "
                         "random-init 40x256 PolicyValueNet",
             "games_per_gpu": G, "n_playout": P, "node_cap": args.node_cap, "cuda_graphs": bool(args.graphs),
             "resident_samples_kept_on_device": resident_samples, "parallelism": f"games sharded x{world}, "

@@ -88,3 +88,37 @@ def test_lockstep_search_4096_games_tree_invariants():
     s.check_status()
     _, v2, _ = s.root_visits()
     assert bool((v2.sum(1) == torch.clamp(kept_visits - 1, min=0) + 8).all())
+
+
+@pytest.mark.parametrize("tap", [(1, 1), (0, 0), (2, 2), (0, 2)])
+def test_conv_full_batch_shifted_identity_is_exact(tap):
+    """K9 at the bench size (4096 boards = 2880 M-tiles): with a weight that is the identity on one filter tap
+    the convolution is a pure board shift with zero padding, so y = relu(shift(x) + bias + skip) must hold
+    EXACTLY in every tile, row and board (fp32 sum of exactly representable terms, one rounding to bf16)."""
+    from chinesechesszero_b200 import _lib
+
+    r, s = tap
+    n = 4096
+    cl = torch.channels_last
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(n, 256, 10, 9, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=cl)
+    skip = torch.randn(n, 256, 10, 9, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=cl)
+    bias = (torch.randn(256, device="cuda", generator=g) * 0.5).to(torch.bfloat16).float()
+    w = torch.zeros(256, 256, 3, 3, device="cuda", dtype=torch.bfloat16)
+    w[torch.arange(256), torch.arange(256), r, s] = 1.0
+    w = w.contiguous(memory_format=cl)
+    # cross-correlation: y[h, w] += x[h + r - 1, w + s - 1]
+    shifted = torch.zeros_like(x, dtype=torch.float32)
+    hs, ws = r - 1, s - 1
+    dst_h = slice(max(0, -hs), 10 - max(0, hs))
+    src_h = slice(max(0, hs), 10 - max(0, -hs))
+    dst_w = slice(max(0, -ws), 9 - max(0, ws))
+    src_w = slice(max(0, ws), 9 - max(0, -ws))
+    shifted[:, :, dst_h, dst_w] = x[:, :, src_h, src_w].float()
+    for sk in (None, skip):
+        ref = shifted + bias.view(1, -1, 1, 1)
+        if sk is not None:
+            ref = ref + sk.float()
+        ref = torch.relu(ref).to(torch.bfloat16)
+        y = _lib.conv3x3_c256(x, w, bias, sk)
+        assert torch.equal(y, ref.contiguous(memory_format=cl))

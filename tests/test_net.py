@@ -83,3 +83,39 @@ def test_bf16_evaluator_within_tolerance(gold, name, conv_impl):
     # tighter sanity bound so the check is not vacuous for near-uniform policies
     logp = torch.log_softmax(logits, 1).cpu().numpy()
     assert np.abs(logp - gold[f"{name}_logp"]).max() < 5e-2
+
+
+def test_stem_tables_reproduce_the_stem_convolution_on_cpu():
+    """K10's lookup tables (net.stem_tables): bias_turn[turn][border class] + the table rows of the occupied
+    3x3 neighbourhood equal conv_block + BN on the search-time planes (net.py:84, 160-177) -- host arithmetic only."""
+    import torch.nn.functional as F
+
+    from chinesechesszero_b200.net import Net, _fold, stem_tables
+    from oracle import cchess_shim as cs
+    from tests.positions import random_playout_positions
+
+    torch.manual_seed(5)
+    net = Net(num_channels=256, resblocks_num=0)
+    net_oracle.perturb_(net.state_dict(), seed=2)
+    net.eval()
+    w, b = _fold(net.conv_block, net.conv_block_bn)
+    w = w.to(torch.bfloat16)  # the evaluator's operand precision
+    table, bias_turn = stem_tables(w, b)
+    table, bias_turn = table.float().numpy(), bias_turn.numpy()
+    recs = random_playout_positions(2, 40, seed=1, every=3)[:24]
+    planes = cs.batch_movegen_encode(recs)[3]  # bf16 bit patterns (n, 10710)
+    x = torch.from_numpy((planes.astype(np.uint32) << 16).view(np.float32).reshape(-1, 119, 10, 9))
+    ref = F.conv2d(x, w.float(), b, padding=1).numpy()
+    assert set(recs[:, 90].tolist()) == {0, 1}
+    for i, rec in enumerate(recs):
+        turn = int(rec[90] != 0)
+        for h in range(10):
+            for wc in range(9):
+                cls = (0 if h == 0 else 2 if h == 9 else 1) * 3 + (0 if wc == 0 else 2 if wc == 8 else 1)
+                acc = bias_turn[turn, cls].copy()
+                for r in range(3):
+                    for s in range(3):
+                        nh, nw = h + r - 1, wc + s - 1
+                        if 0 <= nh <= 9 and 0 <= nw <= 8:
+                            acc += table[r * 3 + s, int(rec[nh * 9 + nw]) & 15]
+                assert np.abs(acc - ref[i, :, h, wc]).max() < 2e-5
