@@ -31,6 +31,12 @@ def metric_name(playouts: int) -> str:
     return f"self-play moves/sec at {playouts} playouts"
 
 
+def workload_name(games: int, playouts: int) -> str:
+    tag = "configs[3] (per-GPU shard of the 8xB200 run)" if (games, playouts) == (8192, 800) else "configs[2]"
+    return (f"{tag}: lockstep batched self-play, {games} concurrent games x {playouts} playouts per GPU, "
+            "random-init 40x256 PolicyValueNet")
+
+
 def ncu_traffic(kernel: str, units: int):
     """dram read+write bytes per launch from the committed ncu capture (profiles/ncu_traffic.json),
     scaled to `units`; None when no capture is recorded for the kernel."""
@@ -158,8 +164,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": metric_name(args.playouts), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init net, torch.manual_seed(0))",
-        "config": {"workload": "reference collect.py path: one self-play game on CPU, random-init PolicyValueNet",
-                   "n_playout": args.playouts, "games": 1},
+        "config": {"workload": workload_name(args.games, args.playouts), "games_per_gpu": args.games, "n_playout": args.playouts,
+                   "sample": "the reference plays its games one after the other (collect.py:138): each step is one move of ONE of the "
+                             f"{args.games} games, {args.playouts} playouts, through the CPU port of collect.py -> game.py -> mcts.py -> "
+                             "net.py (shim board, flat search, fp32 batch-1 forward per playout); moves/s of one game = the reference's "
+                             "whole-job rate on this host"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -422,9 +431,7 @@ def run_own_arm(args):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic (random-init net, torch.manual_seed(0); games from the start position)",
         "config": {
-            "workload": ("configs[3] (per-GPU shard of the 8xB200 run)" if (G, P) == (8192, 800) else "configs[2]")
-                        + f": lockstep batched self-play, {G} concurrent games x {P} playouts per GPU, "
-                        "random-init 40x256 PolicyValueNet",
+            "workload": workload_name(G, P),
             "games_per_gpu": G, "n_playout": P, "node_cap": args.node_cap, "cuda_graphs": bool(args.graphs),
             "resident_samples_kept_on_device": resident_samples, "parallelism": f"games sharded x{world}, "
             "no collective on the hot path",
