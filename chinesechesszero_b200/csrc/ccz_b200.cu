@@ -381,6 +381,9 @@ int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, cons
     int cta_group = variant & 3;
     const int tail_split = !(variant & 4), dbg = (variant >> 3) & 3;
     int pairs = 1 << ((variant >> 5) & 3);
+#ifndef CCZ_CONV_EXPERIMENTS
+    if (dbg) return fail(-1, "ccz_conv3x3_c256: the load-skipping measurement variants need a -DCCZ_CONV_EXPERIMENTS build");
+#endif
     if (variant == 0) { cta_group = 2; pairs = CCZ_CONV_DEFAULT_PAIRS; }
     if (cta_group == 0) cta_group = 2;
     if (cta_group == 3 || pairs > 4 || (cta_group == 1 && pairs != 1))

@@ -150,8 +150,9 @@ int ccz_replay_pack(const uint8_t *d_hist_boards /*[n,8,96]: history slots, most
  * connection (conv1 of a block), d_skip may alias d_y but d_y must not alias d_x.  tcgen05 implicit GEMM
  * with TMA im2col loads.  variant 0 = the library default; otherwise bits 0-1 = CTA group (1: 128x256 tiles per
  * CTA, 2: CTA pairs on 256x256 tiles), bit 2 = no channel-sliced tail round, bits 5-6 = log2 of the CTA pairs
- * per cluster that share (multicast) one weight stage; bits 3-4 are a measurement aid that skips loads and
- * gives WRONG results. */
+ * per cluster that share (multicast) one weight stage; bits 3-4 (skip every other weight / activation load:
+ * WRONG results, energy-sensitivity measurements only) are rejected unless the library was built with
+ * -DCCZ_CONV_EXPERIMENTS. */
 int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, const void *d_skip, void *d_y,
                      int n_boards, int variant, ccz_stream_t s);
 
