@@ -408,8 +408,8 @@ int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, cons
     }
     cudaError_t e;
 #define CCZ_CONV_LAUNCH(CG, PAIRS)                                                                                      \
-    (d_skip ? cv::launch_variant<CG, PAIRS, true>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, tail_split, dbg, s)     \
-            : cv::launch_variant<CG, PAIRS, false>(tx, tw, ts, ty, d_bias, n_tiles, drv.n_sm, tail_split, dbg, s))
+    (d_skip ? cv::launch_variant<CG, PAIRS, true>(tx, tw, ts, ty, d_bias, n_tiles, tail_split, dbg, s)     \
+            : cv::launch_variant<CG, PAIRS, false>(tx, tw, ts, ty, d_bias, n_tiles, tail_split, dbg, s))
     if (cta_group == 1) e = CCZ_CONV_LAUNCH(1, 1);
     else if (pairs == 1) e = CCZ_CONV_LAUNCH(2, 1);
     else if (pairs == 2) e = CCZ_CONV_LAUNCH(2, 2);
@@ -426,10 +426,12 @@ int ccz_stem_lookup(const uint8_t *d_boards, int n, const void *d_table, const f
     if (!d_boards || !d_table || !d_bias_turn || !d_y) return fail(-1, "ccz_stem_lookup: NULL pointer");
     if (((uintptr_t)d_boards & 3) || (((uintptr_t)d_table | (uintptr_t)d_bias_turn | (uintptr_t)d_y) & 15))
         return fail(-1, "ccz_stem_lookup: pointers must be 16-byte aligned (boards 4-byte)");
-    static int n_sm = 0;
+    static int n_sm_dev[64] = {0};
+    int dev = 0;
+    CCZ_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(-1, "ccz_stem_lookup: device index out of range");
+    int &n_sm = n_sm_dev[dev];
     if (!n_sm) {
-        int dev = 0;
-        CCZ_CUDA(cudaGetDevice(&dev));
         CCZ_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         CCZ_CUDA(cudaFuncSetAttribute(st::stem_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::SMEM_BYTES));
     }

@@ -479,7 +479,6 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_
 struct Driver {
     EncodeTiledFn tiled = nullptr;
     EncodeIm2colFn im2col = nullptr;
-    int n_sm = 0;
     bool ready = false;
 };
 
@@ -494,9 +493,6 @@ inline const char *driver_init(Driver &d) {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f)
         return "cuTensorMapEncodeIm2col not available from the driver";
     d.im2col = reinterpret_cast<EncodeIm2colFn>(f);
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-        return "cudaDeviceGetAttribute(MultiProcessorCount) failed";
     d.ready = true;
     return nullptr;
 }
@@ -525,10 +521,17 @@ inline bool encode_im2col(const Driver &d, CUtensorMap *m, const void *ptr, int 
 
 template <int CG, int PAIRS, bool HAS_SKIP>
 inline cudaError_t launch_variant(const CUtensorMap &tx, const CUtensorMap &tw, const CUtensorMap &ts, const CUtensorMap &ty, const float *bias,
-                                  int n_tiles, int n_sm, int tail_split, int dbg, cudaStream_t stream) {
+                                  int n_tiles, int tail_split, int dbg, cudaStream_t stream) {
     auto kern = conv3x3_c256_kernel<CG, PAIRS, HAS_SKIP>;
     constexpr int CLUSTER = CG * PAIRS;
-    static int max_clusters = 0; // resident clusters of this shape (GPC boundaries can strand SMs for CLUSTER > 2)
+    // per device: resident clusters of this shape (GPC boundaries can strand SMs for CLUSTER > 2); function
+    // attributes are per device too
+    static int max_clusters_dev[64] = {0};
+    int dev = 0, n_sm = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    int &max_clusters = max_clusters_dev[dev];
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = Cfg<CG>::SMEM_BYTES;
@@ -541,7 +544,9 @@ inline cudaError_t launch_variant(const CUtensorMap &tx, const CUtensorMap &tw, 
     cfg.attrs = at;
     cfg.numAttrs = 1;
     if (!max_clusters) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::SMEM_BYTES);
+        cudaError_t e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         cfg.gridDim = dim3((unsigned)(n_sm / CLUSTER * CLUSTER));
         int n = 0;

@@ -80,6 +80,10 @@ class Net(nn.Module):
         return policy, value
 
 
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
     """Eval-mode BatchNorm folded into the preceding convolution (fp32 arithmetic)."""
     w = conv.weight.detach().float()
@@ -169,6 +173,16 @@ class BatchedEvaluator:
         self.heads_b = torch.cat([pb, vb], 0).to(dev, dt)
         self.policy_fc = (net.policy_fc.weight.detach().to(dev, dt), net.policy_fc.bias.detach().to(dev, torch.float32))
         self.value_fc1 = (net.value_fc1.weight.detach().to(dev, dt), net.value_fc1.bias.detach().to(dev, dt))
+        # 16-byte-aligned GEMM operands for the two FC layers: K = 17*90 = 1530 and 7*90 = 630 give row strides that
+        # are not multiples of 16 bytes, which sends cuBLAS to a legacy sm80 kernel (113 us for the policy FC at 4096
+        # leaves).  Zero-padded copies: K -> 1536 / 640, policy N -> 2088.
+        self._kp, self._kv, self._np = _round_up(PLAYS * 90, 8), _round_up(PIECES * 90, 8), _round_up(N_ACTIONS, 8)
+        wp = torch.zeros((self._np, self._kp), dtype=dt, device=dev)
+        wp[:N_ACTIONS, :PLAYS * 90] = self.policy_fc[0]
+        wv = torch.zeros((self.value_fc1[0].shape[0], self._kv), dtype=dt, device=dev)
+        wv[:, :PIECES * 90] = self.value_fc1[0]
+        self._fc_pad = (wp, wv)
+        self._head_buf = {}
         self.value_fc2 = (net.value_fc2.weight.detach().to(dev, torch.float32),
                           net.value_fc2.bias.detach().to(dev, torch.float32))
 
@@ -229,10 +243,21 @@ class BatchedEvaluator:
             y = self._conv_relu(x, c1, k9_plain)
             x = self._conv_add_relu(y, c2, x, k9_skip)
         h = F.relu_(F.conv2d(x, self.heads_w, self.heads_b))  # (g, 24, 10, 9)
-        hp = h[:, :PLAYS].reshape(g, PLAYS * 90)               # NCHW flatten order, net.py:97
-        hv = h[:, PLAYS:].reshape(g, PIECES * 90)
-        logits = F.linear(hp, self.policy_fc[0]).float() + self.policy_fc[1]
-        v = F.relu_(F.linear(hv, *self.value_fc1)).float()
+        if self.device.type == "cuda":
+            buf = self._head_buf.get(g)  # [policy operand | value operand], pad columns stay zero
+            if buf is None:
+                buf = self._head_buf[g] = torch.zeros((g, self._kp + self._kv), dtype=h.dtype, device=h.device)
+                if len(self._head_buf) > 8:
+                    self._head_buf.pop(next(iter(self._head_buf)))
+            buf[:, :PLAYS * 90].view(g, PLAYS, 10, 9).copy_(h[:, :PLAYS])  # NCHW flatten order, net.py:97
+            buf[:, self._kp:self._kp + PIECES * 90].view(g, PIECES, 10, 9).copy_(h[:, PLAYS:])
+            logits = F.linear(buf[:, :self._kp], self._fc_pad[0])[:, :N_ACTIONS].float() + self.policy_fc[1]
+            v = F.relu_(F.linear(buf[:, self._kp:], self._fc_pad[1], self.value_fc1[1])).float()
+        else:
+            hp = h[:, :PLAYS].reshape(g, PLAYS * 90)               # NCHW flatten order, net.py:97
+            hv = h[:, PLAYS:].reshape(g, PIECES * 90)
+            logits = F.linear(hp, self.policy_fc[0]).float() + self.policy_fc[1]
+            v = F.relu_(F.linear(hv, *self.value_fc1)).float()
         v = torch.tanh(F.linear(v, *self.value_fc2)).view(g)
         return logits, v
 
