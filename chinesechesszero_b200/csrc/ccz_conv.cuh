@@ -90,6 +90,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Wait for the roles that are a whole tile ahead of their barrier (epilogue warps, skip-tile producer): back off
+// between polls so 130 waiting threads per CTA do not spend issue slots (= power, which is the bound) on a spin loop.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -385,7 +403,7 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
                 const WorkItem wi = work_item(item, n_full, split_log2);
                 const int m0 = ((wi.tile * PAIRS + (int)pair_id) * CG + (int)prank) * BM;
-                mbar_wait(bar_stfree, (it & 1) ^ 1);
+                mbar_wait_relaxed(bar_stfree, (it & 1) ^ 1);
                 mbar_expect_tx(bar_skip, (wi.n_w / 64) * (BM * 128));
                 for (int g = 0; g < wi.n_w / 64; ++g) tma_load_2d<1>(staging + g * (BM * 128), &tm_skip, bar_skip, wi.n_off + g * 64, m0);
             }
@@ -400,8 +418,8 @@ conv3x3_c256_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
             const WorkItem wi = work_item(item, n_full, split_log2);
             const int m0 = ((wi.tile * PAIRS + (int)pair_id) * CG + (int)prank) * BM;
-            if (HAS_SKIP) mbar_wait(bar_skip, it & 1);
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            if (HAS_SKIP) mbar_wait_relaxed(bar_skip, it & 1);
+            mbar_wait_relaxed(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1

@@ -1,6 +1,8 @@
 """Attribute ncu per-SASS-instruction counters to CUDA source lines.
 
   python scripts/ncu_lines.py gpurun_out/prof.ncu-rep <kernel-substring> [top_n]
+  NCU_KID='::regex:<base name>:<n>' (ncu --kernel-id) selects the n-th matching launch on the ncu side when the
+  mangled substring that picks the SASS section cannot serve as ncu's kernel regex (template instances).
 
 Joins `ncu --page source --csv` (SASS view: executed instructions, stall samples) with
 `nvdisasm -g` line markers of the in-tree libccz_b200.so (compiled with -lineinfo)."""
@@ -39,7 +41,7 @@ for ln in dis.splitlines():
     if m:
         line_of[int(m.group(1), 16)] = cur
 
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kern}"], capture_output=True,
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *(["--kernel-id", os.environ["NCU_KID"]] if os.environ.get("NCU_KID") else ["-k", f"regex:{kern}"])], capture_output=True,
                      text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Address" in r and "Source" in r)
