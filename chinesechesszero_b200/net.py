@@ -183,6 +183,12 @@ class BatchedEvaluator:
         wv[:, :PIECES * 90] = self.value_fc1[0]
         self._fc_pad = (wp, wv)
         self._head_buf = {}
+        # the fused 1x1 heads as one GEMM over the NHWC pixel rows: [g*90, C] x [C, 24 -> 32] (+ bias)
+        hw = torch.zeros((32, self.heads_w.shape[1]), dtype=dt, device=dev)
+        hw[:PLAYS + PIECES] = self.heads_w.reshape(PLAYS + PIECES, -1)
+        hb = torch.zeros((32,), dtype=dt, device=dev)
+        hb[:PLAYS + PIECES] = self.heads_b
+        self._heads_gemm = (hw, hb)
         self.value_fc2 = (net.value_fc2.weight.detach().to(dev, torch.float32),
                           net.value_fc2.bias.detach().to(dev, torch.float32))
 
@@ -242,18 +248,22 @@ class BatchedEvaluator:
         for c1, c2 in self.blocks:
             y = self._conv_relu(x, c1, k9_plain)
             x = self._conv_add_relu(y, c2, x, k9_skip)
-        h = F.relu_(F.conv2d(x, self.heads_w, self.heads_b))  # (g, 24, 10, 9)
         if self.device.type == "cuda":
+            # 1x1 heads = a GEMM over the (g*90, C) NHWC pixel rows (a view of the channels_last activations)
+            rows = x.permute(0, 2, 3, 1).reshape(g * 90, x.shape[1])
+            h = F.relu_(F.linear(rows, *self._heads_gemm)).view(g, 90, 32)
             buf = self._head_buf.get(g)  # [policy operand | value operand], pad columns stay zero
             if buf is None:
                 buf = self._head_buf[g] = torch.zeros((g, self._kp + self._kv), dtype=h.dtype, device=h.device)
                 if len(self._head_buf) > 8:
                     self._head_buf.pop(next(iter(self._head_buf)))
-            buf[:, :PLAYS * 90].view(g, PLAYS, 10, 9).copy_(h[:, :PLAYS])  # NCHW flatten order, net.py:97
-            buf[:, self._kp:self._kp + PIECES * 90].view(g, PIECES, 10, 9).copy_(h[:, PLAYS:])
+            # NCHW flatten order (channel-major within a board), net.py:97
+            buf[:, :PLAYS * 90].view(g, PLAYS, 90).copy_(h[:, :, :PLAYS].transpose(1, 2))
+            buf[:, self._kp:self._kp + PIECES * 90].view(g, PIECES, 90).copy_(h[:, :, PLAYS:PLAYS + PIECES].transpose(1, 2))
             logits = F.linear(buf[:, :self._kp], self._fc_pad[0])[:, :N_ACTIONS].float() + self.policy_fc[1]
             v = F.relu_(F.linear(buf[:, self._kp:], self._fc_pad[1], self.value_fc1[1])).float()
         else:
+            h = F.relu_(F.conv2d(x, self.heads_w, self.heads_b))  # (g, 24, 10, 9)
             hp = h[:, :PLAYS].reshape(g, PLAYS * 90)               # NCHW flatten order, net.py:97
             hv = h[:, PLAYS:].reshape(g, PIECES * 90)
             logits = F.linear(hp, self.policy_fc[0]).float() + self.policy_fc[1]
