@@ -402,7 +402,8 @@ def run_own_arm(args):
     step_share = None if args.graphs else fwd_avg * n_fwd / s0.elapsed_time(s1)
     forward = {"kernel": f"bf16 Net.forward over the leaf batch (conv_impl={base_eval.conv_impl}: 3x3 tower on "
                          + ("K9 ccz::conv3x3_c256_kernel" if base_eval.conv_impl.startswith("k9") else "cuDNN")
-                         + ", stem / 1x1 heads / FC through cuDNN + cuBLAS)",
+                         + (", stem on K10 ccz::stem::stem_lookup_kernel from the board records" if not base_eval.needs_planes
+                            else ", stem through cuDNN") + ", 1x1 heads + FC layers as cuBLAS GEMMs)",
                "achieved": tflops, "unit": "TFLOP/s", "frac": tflops / peak_tf, "flop_per_launch": G * FLOP_PER_POSITION,
                "ms_per_launch": fwd_avg, "launches_timed": n_fwd, "share_of_step": step_share}
     conv_flop = 2.0 * G * 90 * 256 * 2304  # one 3x3 256->256 convolution over G boards
@@ -425,7 +426,7 @@ def run_own_arm(args):
         roof = {"bound": "tensor", "achieved": tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": tflops / peak_tf,
                 "traffic": None, "peak_source": peaks["source"] + " sustained", **{k: v for k, v in forward.items()
                                                                                    if k not in ("achieved", "unit", "frac")}}
-    k9_per_fwd = {"k9": 80, "k9_skip": 40}.get(base_eval.conv_impl, 0)
+    k9_per_fwd = {"k9": 80, "k9_skip": 40}.get(base_eval.conv_impl, 0) + (0 if base_eval.needs_planes else 1)  # + K10
     line = {
         "metric": metric_name(P), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
