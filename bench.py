@@ -273,8 +273,8 @@ def bench_train(torch, batch: int = 512, steps: int = 5):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"workload": f"configs[4]: PolicyValueNet train step, bf16 autocast, batch {batch} (old/new policy eval, "
-                        "weight+optimizer backup, fwd/bwd, clip 5.0, Adam, KL)", "value": batch / ms * 1e3,
+    return {"workload": f"configs[4]: PolicyValueNet train step, bf16 autocast, channels_last weights, batch {batch} (old/new "
+                        "policy eval, weight+optimizer backup, fwd/bwd, clip 5.0, Adam, KL)", "value": batch / ms * 1e3,
             "unit": "samples/s", "ms_per_step": ms, "loss": last["loss"], "kl": last["kl"]}
 
 

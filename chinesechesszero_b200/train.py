@@ -67,6 +67,10 @@ class TrainPipeline:
             self.policy_value_net = PolicyValueNet(model=init_model, **net_kwargs) if init_model else PolicyValueNet(**net_kwargs)
         except Exception:
             self.policy_value_net = PolicyValueNet(**net_kwargs)  # train.py:66-78
+        # NHWC weights: cuDNN's bf16 tensor-core kernels are channels-last; with NCHW parameters every convolution
+        # of the forward and backward pass is wrapped in layout transposes.  state_dict keys / values are unchanged.
+        if self.policy_value_net.device.type == "cuda" and os.environ.get("CCZ_TRAIN_CHANNELS_LAST", "1") != "0":
+            self.policy_value_net.policy_value_net.to(memory_format=torch.channels_last)
         self.dataset = None
         self.last_kl = 0.0
 
