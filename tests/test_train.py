@@ -74,3 +74,45 @@ def test_policy_update_runs_over_npy_replay(tmp_path):
     with pytest.raises(ValueError):
         pipe.train_step(torch.tensor(states, dtype=torch.float32), torch.tensor(bad, dtype=torch.float32),
                         torch.tensor(winners, dtype=torch.float32))
+
+
+def test_step_backup_restores_weights_and_optimizer_state():
+    """The rollback copy (train.py:155-163, 200-206): after restore() the weights, BN statistics, Adam moments and step
+    counters are the ones saved before the step -- also when the step being undone was the optimizer's first."""
+    from chinesechesszero_b200.train import TrainPipeline
+
+    states, probs, winners = train_batch(8)
+    torch.manual_seed(2)
+    pipe = TrainPipeline(batch_size=8, net_kwargs=dict(num_channels=16, resblocks_num=1))
+    pv = pipe.policy_value_net
+    net, opt = pv.policy_value_net, pv.optimizer
+    batch = tuple(torch.tensor(a, dtype=torch.float32) for a in (states, probs, winners))
+
+    def snapshot():
+        return ({k: v.clone() for k, v in net.state_dict().items()},
+                {i: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()} for i, st in
+                 enumerate(opt.state[p] for g in opt.param_groups for p in g["params"] if p in opt.state)})
+
+    # first step: the optimizer has no state yet
+    w0, s0 = snapshot()
+    assert not s0
+    pipe.train_step(*batch)
+    assert len(opt.state) > 0
+    pipe._backup.restore(net, opt)
+    w1, s1 = snapshot()
+    assert not s1 and all(torch.equal(w0[k], w1[k]) for k in w0)
+    # later step: moments and step counters come back
+    pipe.train_step(*batch)
+    pipe.train_step(*batch)
+    w2, s2 = snapshot()
+    r = pipe.train_step(*batch)   # backs up (w2, s2), then steps
+    assert not r["rolled_back"]
+    w_after, _ = snapshot()
+    assert any(not torch.equal(w2[k], w_after[k]) for k in w2)
+    pipe._backup.restore(net, opt)
+    w3, s3 = snapshot()
+    assert all(torch.equal(w2[k], w3[k]) for k in w2)
+    assert s2.keys() == s3.keys()
+    for i in s2:
+        for k, v in s2[i].items():
+            assert torch.equal(v, s3[i][k]) if torch.is_tensor(v) else v == s3[i][k]
