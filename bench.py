@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--no-train", action="store_true", help="skip the configs[4] train-step section")
     ap.add_argument("--graphs", action="store_true",
                     help="replay the lockstep step from CUDA graphs (the forward is then timed in a separate loop)")
-    ap.add_argument("--cpu-moves", type=int, default=1, help="moves of the CPU-port sample")
+    ap.add_argument("--cpu-moves", type=int, default=3, help="moves of the CPU-port sample (SURVEY 8d: the first 3 moves, ~16 s)")
     ap.add_argument("--conv-impl", default=None, choices=["k9", "k9_skip", "cudnn"],
                     help="tower convolution kernel (default: the evaluator's default, K9 = csrc/ccz_conv.cuh)")
     ap.add_argument("--conv-sample", type=int, default=8, help="bracket every K9 launch of every n-th forward with CUDA events")
