@@ -18,6 +18,20 @@
 //     -> TMA store.
 // Warp roles (256 threads): 0 = A/B TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = skip-tile
 // producer, 4..7 = epilogue.
+//
+// mbarriers (per CTA; "leader" = the even CTA of a pair, the only one that issues MMAs):
+//   full[s]   count 1 + tx bytes : both CTAs' TMA loads of stage s complete on the LEADER's barrier, which expects
+//                                   the bytes of the whole pair; the MMA issuer waits on it
+//   empty[s]  count PAIRS        : tcgen05.commit of the MMAs that read stage s, multicast to every CTA whose producer
+//                                   may overwrite it (the pair; the whole cluster when weight stages are shared)
+//   tfull[a]  count 1            : tcgen05.commit after the last k-block of a tile, multicast to the pair -> epilogue
+//   tempty[a] count 4 * CG       : lane 0 of each epilogue warp of both CTAs, after its tcgen05.ld's -> MMA issuer
+//   skip      count 1 + tx bytes : the skip tile has landed in the staging buffer -> epilogue
+//   stfree    count 1            : the TMA store of the previous tile has finished READING the staging buffer
+//                                   -> skip-tile producer (the epilogue warps themselves re-sync on bar.sync 1)
+// Everything is persistent: grid = one CTA per SM, static round-robin over work items, phases tracked per role.
+// Under the 1 kW cap the kernel is bound by energy per FLOP, not by issue slots or utilisation (DESIGN.md
+// "K9 in detail" lists what was measured: tail slicing, load skipping, weight multicast, back-off waits).
 #pragma once
 
 #include <cuda.h> // CUtensorMap + enums only; the encode functions are fetched at run time (no -lcuda)
