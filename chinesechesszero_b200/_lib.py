@@ -29,7 +29,7 @@ CONV_VARIANT_1CTA, CONV_VARIANT_PAIR, CONV_VARIANT_2PAIRS, CONV_VARIANT_4PAIRS =
 EXPORTS = (
     "ccz_version", "ccz_last_error", "ccz_init", "ccz_action_table", "ccz_boards_start",
     "ccz_movegen_encode", "ccz_board_keys_init", "ccz_board_push", "ccz_mcts_reset", "ccz_mcts_select",
-    "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack", "ccz_conv3x3_c256", "ccz_stem_lookup",
+    "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack", "ccz_conv3x3_c256", "ccz_conv3x3_plan", "ccz_stem_lookup",
 )
 
 
@@ -101,6 +101,7 @@ def load() -> ctypes.CDLL:
     lib.ccz_replay_pack.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.ccz_conv3x3_c256.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     lib.ccz_stem_lookup.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.ccz_conv3x3_plan.argtypes = [i32, i32, i32, vp]
     for name in EXPORTS:
         if name not in ("ccz_last_error",):
             getattr(lib, name).restype = i32
@@ -332,3 +333,11 @@ def stem_lookup(boards: torch.Tensor, table: torch.Tensor, bias_turn: torch.Tens
         check(load().ccz_stem_lookup(_ptr(boards), n, _ptr(table), _ptr(bias_turn), out.data_ptr(), stream_ptr(boards.device)),
               "ccz_stem_lookup")
     return out
+
+
+def conv3x3_plan(n_boards: int, variant: int = 0, resident_clusters: int = 74) -> dict:
+    """Host-side work plan of K9 for ``n_boards`` (no device needed): see ``ccz_conv3x3_plan``."""
+    out = (ctypes.c_int32 * 6)()
+    check(load().ccz_conv3x3_plan(int(n_boards), int(variant), int(resident_clusters), out), "ccz_conv3x3_plan")
+    keys = ("rows_per_tile", "n_tiles", "n_items", "n_full", "split_log2", "clusters")
+    return dict(zip(keys, (int(v) for v in out)))

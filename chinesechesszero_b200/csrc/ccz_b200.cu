@@ -419,6 +419,22 @@ int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, cons
     return 0;
 }
 
+int ccz_conv3x3_plan(int n_boards, int variant, int resident_clusters, int32_t *out) {
+    namespace cv = ccz::conv;
+    if (n_boards <= 0 || resident_clusters <= 0 || !out || variant < 0 || variant >= 128)
+        return fail(-1, "ccz_conv3x3_plan: bad argument");
+    int cta_group = variant & 3, pairs = 1 << ((variant >> 5) & 3);
+    if (variant == 0) { cta_group = 2; pairs = CCZ_CONV_DEFAULT_PAIRS; }
+    if (cta_group == 0) cta_group = 2;
+    if (cta_group == 3 || pairs > 4 || (cta_group == 1 && pairs != 1)) return fail(-1, "ccz_conv3x3_plan: unsupported variant");
+    const long long m = (long long)n_boards * cv::BOARD_HW;
+    const int rows_per_tile = cv::BM * cta_group * pairs;
+    const int n_tiles = (int)((m + rows_per_tile - 1) / rows_per_tile);
+    const cv::Plan pl = cv::plan_items(n_tiles, resident_clusters, !(variant & 4));
+    out[0] = rows_per_tile; out[1] = n_tiles; out[2] = pl.n_items; out[3] = pl.n_full; out[4] = pl.split_log2; out[5] = pl.clusters;
+    return 0;
+}
+
 int ccz_stem_lookup(const uint8_t *d_boards, int n, const void *d_table, const float *d_bias_turn, void *d_y, ccz_stream_t s) {
     namespace st = ccz::stem;
     if (n < 0) return fail(-1, "ccz_stem_lookup: n < 0");

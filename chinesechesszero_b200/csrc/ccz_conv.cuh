@@ -551,6 +551,25 @@ inline bool encode_im2col(const Driver &d, CUtensorMap *m, const void *ptr, int 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Work plan of one launch: `n_tiles` cluster tiles over `clusters` resident clusters.  The tiles of the last, partial
+// round are sliced into 2 or 4 output-channel slices while every slice still gets its own cluster.
+struct Plan {
+    int n_items, n_full, split_log2, clusters;
+};
+inline Plan plan_items(int n_tiles, int clusters, bool tail_split) {
+    const int rem = n_tiles % clusters;
+    int split_log2 = 0;
+    if (tail_split && rem > 0) {
+        while (split_log2 < 2 && (rem << (split_log2 + 1)) <= clusters) ++split_log2;
+    }
+    Plan p;
+    p.split_log2 = split_log2;
+    p.n_full = split_log2 ? n_tiles - rem : n_tiles;
+    p.n_items = p.n_full + (split_log2 ? rem << split_log2 : 0);
+    p.clusters = clusters > p.n_items ? p.n_items : clusters;
+    return p;
+}
+
 template <int CG, int PAIRS, bool HAS_SKIP>
 inline cudaError_t launch_variant(const CUtensorMap &tx, const CUtensorMap &tw, const CUtensorMap &ts, const CUtensorMap &ty, const float *bias,
                                   int n_tiles, int tail_split, int dbg, cudaStream_t stream) {
@@ -587,19 +606,9 @@ inline cudaError_t launch_variant(const CUtensorMap &tx, const CUtensorMap &tw, 
         if (n < 1) return cudaErrorInvalidConfiguration;
         max_clusters = n < n_sm / CLUSTER ? n : n_sm / CLUSTER;
     }
-    int clusters = max_clusters;
-    // tail split: the last round has `rem` tiles for `clusters` clusters; slice them by output channels
-    // while every slice still gets its own cluster
-    const int rem = n_tiles % clusters;
-    int split_log2 = 0;
-    if (tail_split && rem > 0) {
-        while (split_log2 < 2 && (rem << (split_log2 + 1)) <= clusters) ++split_log2;
-    }
-    const int n_full = split_log2 ? n_tiles - rem : n_tiles;
-    const int n_items = n_full + (split_log2 ? rem << split_log2 : 0);
-    if (clusters > n_items) clusters = n_items;
-    cfg.gridDim = dim3((unsigned)(clusters * CLUSTER));
-    return cudaLaunchKernelEx(&cfg, kern, tx, tw, ts, ty, bias, n_items, n_full, split_log2, dbg);
+    const Plan pl = plan_items(n_tiles, max_clusters, tail_split != 0);
+    cfg.gridDim = dim3((unsigned)(pl.clusters * CLUSTER));
+    return cudaLaunchKernelEx(&cfg, kern, tx, tw, ts, ty, bias, pl.n_items, pl.n_full, pl.split_log2, dbg);
 }
 
 } // namespace conv

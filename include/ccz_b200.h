@@ -156,6 +156,13 @@ int ccz_replay_pack(const uint8_t *d_hist_boards /*[n,8,96]: history slots, most
 int ccz_conv3x3_c256(const void *d_x, const void *d_w, const float *d_bias, const void *d_skip, void *d_y,
                      int n_boards, int variant, ccz_stream_t s);
 
+/* Host-only: the work plan ccz_conv3x3_c256 would launch for n_boards on a device with `resident_clusters`
+ * co-resident clusters of the variant's shape (74 CTA pairs on a B200).  out[6] = {pixel rows per cluster tile,
+ * cluster tiles, work items, whole-tile items, log2 of the channel slices of the last partial round, clusters
+ * launched}.  Work item i < out[3] is tile i over all 256 channels; item out[3] + j is channel slice
+ * j % 2^out[4] (256 >> out[4] channels) of tile out[3] + (j >> out[4]); cluster c runs items c, c + out[5], ... */
+int ccz_conv3x3_plan(int n_boards, int variant, int resident_clusters, int32_t *out);
+
 /* K10: the stem convolution of Net.forward (conv_block 119->256 + BN + ReLU, net.py:84) for SEARCH-TIME
  * inputs, computed from the board records themselves.  policy_value_fn (net.py:160-177) feeds 7 zero
  * history states + the current one-hot piece planes + a constant turn plane, so each output pixel is

@@ -78,3 +78,36 @@ def test_header_is_valid_c_and_matches_ctypes_struct(tmp_path):
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == ctypes.sizeof(_lib.ArenaStruct)
     assert [int(x) for x in out[1:]] == [_lib.BOARD_BYTES, _lib.N_ACTIONS, _lib.FLAG_TIE_MASK]
+
+
+def test_conv_work_plan_covers_every_tile_and_channel_exactly_once():
+    """K9's persistent schedule (host logic of ccz_conv3x3_c256, csrc/ccz_conv.cuh): whole tiles round-robin over the
+    resident clusters, the last partial round sliced by output channels.  Every (tile, channel) must be produced by
+    exactly one work item, slices may only appear in the last round, and no cluster gets more than one slice."""
+    from chinesechesszero_b200 import _lib
+
+    for variant, clusters in ((0, 74), (2, 74), (1, 148), (34, 34), (66, 16), (6, 74)):
+        for n in (1, 2, 3, 37, 90, 128, 300, 777, 1024, 2048, 4096, 8192, 12345):
+            p = _lib.conv3x3_plan(n, variant, clusters)
+            assert p["n_tiles"] == -(-n * 90 // p["rows_per_tile"])
+            split = 1 << p["split_log2"]
+            assert p["n_full"] <= p["n_tiles"] and p["n_items"] == p["n_full"] + (p["n_tiles"] - p["n_full"]) * split
+            cover = {}
+            for i in range(p["n_items"]):
+                if i < p["n_full"]:
+                    tile, lo, width = i, 0, 256
+                else:
+                    j = i - p["n_full"]
+                    width = 256 >> p["split_log2"]
+                    tile, lo = p["n_full"] + (j >> p["split_log2"]), (j & (split - 1)) * width
+                for c in range(lo, lo + width, 64):
+                    assert (tile, c) not in cover
+                    cover[(tile, c)] = i
+            assert len(cover) == p["n_tiles"] * 4 and {t for t, _ in cover} == set(range(p["n_tiles"]))
+            assert 1 <= p["clusters"] <= min(clusters, p["n_items"])
+            if split > 1:
+                assert variant != 6                                    # bit 2 switches the slicing off
+                assert p["n_full"] % clusters == 0                     # whole rounds first
+                assert p["n_items"] - p["n_full"] <= clusters          # the sliced round fits one pass
+            rounds = -(-p["n_items"] // p["clusters"])
+            assert rounds == -(-p["n_tiles"] // clusters) or split > 1
