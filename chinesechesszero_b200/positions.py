@@ -34,9 +34,13 @@ def perft_levels(depth: int, device="cuda"):
     return out
 
 
-def perft_count(depth: int, device="cuda") -> int:
-    """perft(depth) = number of leaf nodes: expand depth-1 levels, sum the move counts of the last."""
-    level = _lib.boards_start(1, device)
+def perft_count(depth: int, device="cuda", root=None) -> int:
+    """perft(depth) = number of leaf nodes: expand depth-1 levels, sum the move counts of the last.  ``root``: a
+    96-byte board record (default: the start position)."""
+    if root is None:
+        level = _lib.boards_start(1, device)
+    else:
+        level = torch.as_tensor(np.ascontiguousarray(root, dtype=np.uint8).reshape(1, _lib.BOARD_BYTES)).to(device)
     for _ in range(depth - 1):
         level, _ = expand_level(level)
     _, counts, _, _ = _lib.movegen_encode(level, planes=False)

@@ -90,3 +90,21 @@ EDGE_CASES = [
 
 def edge_case_records() -> np.ndarray:
     return np.stack([record_from_fen(f, c, r) for _, f, c, r in EDGE_CASES])
+
+
+# Published Xiangqi perft results beyond the start position (the perft suite circulated with the chessprogramming
+# wiki's "Chinese Chess Perft Results": mid- and end-game positions with pins, cannon screens, blocked horses and
+# elephants, flying-general lines).  FEN (rank 9 first, 'w' = RED to move) -> perft(1..5).  All 50 values are
+# reproduced by the plain-C oracle and by K1 + K2 on the device; they pin the LEGAL-MOVE SETS (not the order).
+PERFT_SUITE = {
+    "r1ba1a3/4kn3/2n1b4/pNp1p1p1p/4c4/6P2/P1P2R2P/1CcC5/9/2BAKAB2 w": (38, 1128, 43929, 1339047, 53112976),
+    "1cbak4/9/n2a5/2p1p3p/5cp2/2n2N3/6PCP/3AB4/2C6/3A1K1N1 w": (7, 281, 8620, 326201, 10369923),
+    "5a3/3k5/3aR4/9/5r3/5n3/9/3A1A3/5K3/2BC2B2 w": (25, 424, 9850, 202884, 4739553),
+    "CRN1k1b2/3ca4/4ba3/9/2nr5/9/9/4B4/4A4/4KA3 w": (28, 516, 14808, 395483, 11842230),
+    "R1N1k1b2/9/3aba3/9/2nr5/2B6/9/4B4/4A4/4KA3 w": (21, 364, 7626, 162837, 3500505),
+    "C1nNk4/9/9/9/9/9/n1pp5/B3C4/9/3A1K3 w": (28, 222, 6241, 64971, 1914306),
+    "4ka3/4a4/9/9/4N4/p8/9/4C3c/7n1/2BK5 w": (23, 345, 8124, 149272, 3513104),
+    "2b1ka3/9/b3N4/4n4/9/9/9/4C4/2p6/2BK5 w": (21, 195, 3883, 48060, 933096),
+    "1C2ka3/9/C1Nab1n2/p3p3p/6p2/9/P3P3P/3AB4/3p2c2/c1BAK4 w": (30, 830, 22787, 649866, 17920736),
+    "CnN1k1b2/c3a4/4ba3/9/2nr5/9/9/4C4/4A4/4KA3 w": (19, 583, 11714, 376467, 8148177),
+}

@@ -108,3 +108,14 @@ def test_device_perft_counts_and_order():
     assert np.array_equal(levels[2].cpu().numpy(), positions.perft_leaves(3))
     assert dev_positions.perft_count(4) == 3290240
     assert dev_positions.perft_count(5) == 133312995
+
+
+def test_device_perft_published_suite():
+    """K1 + K2 on the ten published perft positions (tests/positions.PERFT_SUITE), depths 1-5: the device move
+    generator and push reproduce all 50 known answers (53 M leaves for the largest)."""
+    from chinesechesszero_b200 import positions as dev_positions
+
+    for fen, expect in positions.PERFT_SUITE.items():
+        rec = positions.record_from_fen(fen)
+        for depth, want in enumerate(expect, start=1):
+            assert dev_positions.perft_count(depth, root=rec) == want, (fen, depth)

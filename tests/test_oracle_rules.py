@@ -126,3 +126,17 @@ def test_planes_layout_matches_policy_value_fn():
     rec_b[90] = 0
     _, _, _, planes_b = cs.batch_movegen_encode(rec_b[None])
     assert (planes_b[0].reshape(17, 7, 10, 9)[16] == 0).all()
+
+
+@pytest.mark.parametrize("fen", list(__import__("tests.positions", fromlist=["PERFT_SUITE"]).PERFT_SUITE))
+def test_published_perft_suite(fen):
+    """Ten published mid-/end-game perft positions, depths 1-5 (50 known answers): pins the oracle's legal-move
+    sets on positions with pins, cannon screens, blocked horses / elephants and flying-general lines."""
+    from tests.positions import PERFT_SUITE, record_from_fen
+
+    rec = record_from_fen(fen)
+    expect = PERFT_SUITE[fen]
+    for depth, want in enumerate(expect, start=1):
+        if want > 20_000_000:  # keep the CPU suite short: the two largest depth-5 counts run in the GPU test
+            continue
+        assert cs.perft(rec, depth) == want, (fen, depth)
