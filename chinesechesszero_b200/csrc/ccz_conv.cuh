@@ -40,6 +40,10 @@
 
 #include <cstdint>
 
+#ifndef CCZ_CONV_BACKOFF_NS
+#define CCZ_CONV_BACKOFF_NS 256 // poll interval of the roles that wait a whole tile ahead
+#endif
+
 namespace ccz {
 namespace conv {
 
@@ -119,7 +123,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(256);
+        __nanosleep(CCZ_CONV_BACKOFF_NS);
     }
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
