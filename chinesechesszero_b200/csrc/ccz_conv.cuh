@@ -108,8 +108,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// Wait for the roles that are a whole tile ahead of their barrier (epilogue warps, skip-tile producer): back off
-// between polls so 130 waiting threads per CTA do not spend issue slots (= power, which is the bound) on a spin loop.
+// Wait for the roles that are a whole tile ahead of their barrier (epilogue warps, skip-tile producer): sleep between
+// polls instead of spinning.  Measured neutral (try_wait already suspends the warp in hardware); kept because it costs
+// nothing and these roles have a whole main loop of slack.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     for (;;) {
         uint32_t done;
