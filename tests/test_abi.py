@@ -111,3 +111,29 @@ def test_conv_work_plan_covers_every_tile_and_channel_exactly_once():
                 assert p["n_items"] - p["n_full"] <= clusters          # the sliced round fits one pass
             rounds = -(-p["n_items"] // p["clusters"])
             assert rounds == -(-p["n_tiles"] // clusters) or split > 1
+
+
+def test_split_evaluator_routes_each_half_to_its_net():
+    """evaluate.SplitEvaluator (host logic of the evaluation match): leaves [0, split) go to the first evaluator,
+    the rest to the second; swapped() exchanges them; planes may be None (evaluators that read the boards)."""
+    import torch
+
+    from chinesechesszero_b200 import _lib
+    from chinesechesszero_b200.evaluate import SplitEvaluator
+
+    def make(tag, needs_planes):
+        def ev(planes, boards):
+            assert (planes is None) == (not needs_planes) or planes is not None
+            n = boards.shape[0]
+            return torch.full((n, 2086), float(tag)), _lib.POLICY_LOGITS, torch.full((n,), float(tag))
+        ev.needs_planes = needs_planes
+        return ev
+
+    a, b = make(1, False), make(2, False)
+    boards = torch.zeros((6, 96), dtype=torch.uint8)
+    s = SplitEvaluator(a, b, 2)
+    assert s.needs_planes is False
+    pol, kind, val = s(None, boards)
+    assert kind == _lib.POLICY_LOGITS and val.tolist() == [1, 1, 2, 2, 2, 2] and pol.shape == (6, 2086)
+    assert s.swapped()(None, boards)[2].tolist() == [2, 2, 1, 1, 1, 1]
+    assert SplitEvaluator(a, make(3, True), 3).needs_planes is True
