@@ -1,8 +1,8 @@
 """``convert.py`` of the reference (convert.py:21-105): ``data.h5`` -> ``states.npy`` / ``mcts.npy`` /
 ``winners.npy`` / ``meta.json``, the form ``train.py:95-100`` memory-maps.  Same function name, defaults,
 output names, dtypes (winners become float32, convert.py:67) and meta keys; the file is read with the
-in-tree HDF5 reader (``h5lite``) because h5py / libhdf5 do not exist in this image; the arrays are
-written through ``numpy.lib.format.open_memmap`` (one game resident at a time on the output side)."""
+in-tree HDF5 reader (``h5lite``, memory-mapped) because h5py / libhdf5 do not exist in this image; the arrays
+are written through ``numpy.lib.format.open_memmap``, so one game at a time is resident on either side."""
 from __future__ import annotations
 
 import json

@@ -20,6 +20,7 @@ which is unavailable here.
 from __future__ import annotations
 
 import os
+import mmap
 import struct
 import zlib
 
@@ -224,7 +225,10 @@ class H5Writer:
 class H5Reader:
     def __init__(self, path: str):
         self.f = open(path, "rb")
-        self.buf = self.f.read()
+        try:  # map instead of read: replay files grow to tens of GB, only the touched pages become resident
+            self.buf = mmap.mmap(self.f.fileno(), 0, access=mmap.ACCESS_READ)
+        except ValueError:  # empty file
+            self.buf = self.f.read()
         if self.buf[:8] != SIGNATURE:
             raise ValueError("not an HDF5 file")
         if self.buf[8] != 0 or self.buf[13] != 8 or self.buf[14] != 8:
@@ -237,6 +241,11 @@ class H5Reader:
         return self
 
     def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        if isinstance(self.buf, mmap.mmap):
+            self.buf.close()
         self.f.close()
 
     # ---- object headers ------------------------------------------------------------------
@@ -261,7 +270,7 @@ class H5Reader:
     def _heap_string(self, heap_addr: int, off: int) -> str:
         assert self.buf[heap_addr:heap_addr + 4] == b"HEAP"
         data_addr = struct.unpack_from("<Q", self.buf, heap_addr + 24)[0]
-        end = self.buf.index(b"\0", data_addr + off)
+        end = self.buf.find(b"\0", data_addr + off)
         return self.buf[data_addr + off:end].decode()
 
     def _walk_group_btree(self, addr: int, heap: int, out: dict):
