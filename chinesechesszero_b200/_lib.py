@@ -22,13 +22,19 @@ KEY_WINDOW = 128
 
 FLAG_CHECK, FLAG_NOMOVES, FLAG_INSUFFICIENT, FLAG_FOURFOLD, FLAG_SIXTY = 1, 2, 4, 8, 16
 FLAG_TIE_MASK = FLAG_INSUFFICIENT | FLAG_FOURFOLD | FLAG_SIXTY
-STATUS_NODE_OVERFLOW = 1
+STATUS_EXPAND_FAILED, STATUS_TREE_DROPPED = 1, 2
+STATUS_NODE_OVERFLOW = STATUS_EXPAND_FAILED
+ADVANCE_NEW_GAME, ADVANCE_DROP_TREE = -1, -2
+CTL_HEAD, CTL_TAIL, CTL_EXPAND_FAILED, CTL_TREES_DROPPED, CTL_MIN_FREE, CTL_WORDS = 0, 1, 2, 3, 4, 8
+NODE_BYTES = 24  # ccz_node (16) + ccz_link (8)
+MAX_CHILDREN = 119  # most legal moves of any Xiangqi position
 POLICY_PROBS, POLICY_LOGITS = 0, 1
 CONV_VARIANT_1CTA, CONV_VARIANT_PAIR, CONV_VARIANT_2PAIRS, CONV_VARIANT_4PAIRS = 1, 2, 2 | 32, 2 | 64
 
 EXPORTS = (
     "ccz_version", "ccz_last_error", "ccz_init", "ccz_action_table", "ccz_boards_start",
-    "ccz_movegen_encode", "ccz_board_keys_init", "ccz_board_push", "ccz_mcts_reset", "ccz_mcts_select",
+    "ccz_movegen_encode", "ccz_board_keys_init", "ccz_board_push", "ccz_mcts_pool_init", "ccz_mcts_reset",
+    "ccz_mcts_reserve", "ccz_mcts_migrate", "ccz_mcts_select",
     "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack", "ccz_conv3x3_c256", "ccz_conv3x3_plan", "ccz_stem_lookup",
 )
 
@@ -42,14 +48,20 @@ class ArenaStruct(ctypes.Structure):
 
     _fields_ = [
         ("n_games", ctypes.c_int32),
-        ("node_cap", ctypes.c_int32),
-        ("d_visits", ctypes.c_void_p),
-        ("d_value", ctypes.c_void_p),
-        ("d_prior", ctypes.c_void_p),
-        ("d_move", ctypes.c_void_p),
-        ("d_first_child", ctypes.c_void_p),
-        ("d_n_child", ctypes.c_void_p),
-        ("d_parent", ctypes.c_void_p),
+        ("n_pages", ctypes.c_int32),
+        ("page_shift", ctypes.c_int32),
+        ("max_pages", ctypes.c_int32),
+        ("d_nodes", ctypes.c_void_p),
+        ("d_links", ctypes.c_void_p),
+        ("d_free_ring", ctypes.c_void_p),
+        ("d_pool_ctl", ctypes.c_void_p),
+        ("d_page_list", ctypes.c_void_p),
+        ("d_page_fill", ctypes.c_void_p),
+        ("d_n_pages", ctypes.c_void_p),
+        ("d_n_pages_new", ctypes.c_void_p),
+        ("d_list_sel", ctypes.c_void_p),
+        ("d_alloc_page", ctypes.c_void_p),
+        ("d_alloc_off", ctypes.c_void_p),
         ("d_root", ctypes.c_void_p),
         ("d_n_nodes", ctypes.c_void_p),
         ("d_status", ctypes.c_void_p),
@@ -93,11 +105,14 @@ def load() -> ctypes.CDLL:
     lib.ccz_movegen_encode.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.ccz_board_keys_init.argtypes = [vp, i32, vp, vp]
     lib.ccz_board_push.argtypes = [vp, vp, i32, vp, vp]
+    lib.ccz_mcts_pool_init.argtypes = [ctypes.POINTER(ArenaStruct), vp]
     lib.ccz_mcts_reset.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp]
+    lib.ccz_mcts_reserve.argtypes = [ctypes.POINTER(ArenaStruct), i32, vp]
+    lib.ccz_mcts_migrate.argtypes = [ctypes.POINTER(ArenaStruct), ctypes.POINTER(ArenaStruct), vp]
     lib.ccz_mcts_select.argtypes = [ctypes.POINTER(ArenaStruct), f32, vp, vp, vp]
     lib.ccz_mcts_expand_backup.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp, i32, vp, vp, vp, vp, vp]
     lib.ccz_mcts_root_visits.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp, vp, vp]
-    lib.ccz_mcts_advance.argtypes = [ctypes.POINTER(ArenaStruct), ctypes.POINTER(ArenaStruct), vp, vp]
+    lib.ccz_mcts_advance.argtypes = [ctypes.POINTER(ArenaStruct), vp, vp]
     lib.ccz_replay_pack.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.ccz_conv3x3_c256.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     lib.ccz_stem_lookup.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -191,41 +206,87 @@ def board_push(boards: torch.Tensor, move_ids: torch.Tensor, keys: torch.Tensor 
               "ccz_board_push")
 
 
-class Arena:
-    """Device arrays of one flat MCTS arena (see ``ccz_arena`` in include/ccz_b200.h)."""
+def search_pages(n_playout: int, page_shift: int) -> int:
+    """Upper bound of the pages one game can take during ``n_playout`` playouts: every playout expands
+    at most one leaf into at most MAX_CHILDREN contiguous slots, a page holds at least
+    ``2**page_shift // MAX_CHILDREN`` such runs, plus the partly used page the search starts in."""
+    runs_per_page = max(1, (1 << page_shift) // MAX_CHILDREN)
+    return -(-int(n_playout) // runs_per_page) + 1
 
-    def __init__(self, n_games: int, node_cap: int, device="cuda"):
-        self.n_games, self.node_cap = int(n_games), int(node_cap)
+
+class Arena:
+    """Device arrays of one pooled MCTS arena (see ``ccz_arena`` in include/ccz_b200.h): ``n_pages``
+    pages of ``2**page_shift`` nodes shared by ``n_games`` trees."""
+
+    def __init__(self, n_games: int, n_pages: int, page_shift: int = 11, max_pages: int | None = None, device="cuda"):
+        self.n_games, self.n_pages, self.page_shift = int(n_games), int(n_pages), int(page_shift)
+        if not 7 <= self.page_shift <= 16:
+            raise CczError("page_shift must be 7..16")
+        if self.n_pages < self.n_games:
+            raise CczError("the pool needs at least one page per game")
+        if (self.n_pages << self.page_shift) >= 1 << 31:
+            raise CczError("pool too large: n_pages << page_shift must stay below 2^31 nodes")
+        self.max_pages = int(max_pages) if max_pages is not None else min(self.n_pages, 4096)
         self.device = torch.device(device)
-        total = self.n_games * self.node_cap
-        z = dict(device=self.device)
-        self.visits = torch.zeros(total, dtype=torch.int32, **z)
-        self.value = torch.zeros(total, dtype=torch.float32, **z)
-        self.prior = torch.zeros(total, dtype=torch.float32, **z)
-        self.move = torch.zeros(total, dtype=torch.int16, **z)
-        self.first_child = torch.zeros(total, dtype=torch.int32, **z)
-        self.n_child = torch.zeros(total, dtype=torch.int16, **z)
-        self.parent = torch.zeros(total, dtype=torch.int32, **z)
-        self.root = torch.zeros(self.n_games, dtype=torch.int32, **z)
-        self.n_nodes = torch.zeros(self.n_games, dtype=torch.int32, **z)
-        self.status = torch.zeros(self.n_games, dtype=torch.int32, **z)
-        self.root_boards = torch.zeros((self.n_games, BOARD_BYTES), dtype=torch.uint8, **z)
-        self.root_keys = torch.zeros((self.n_games, KEY_WINDOW), dtype=torch.int64, **z)
-        self.struct = ArenaStruct(
-            self.n_games, self.node_cap, self.visits.data_ptr(), self.value.data_ptr(), self.prior.data_ptr(),
-            self.move.data_ptr(), self.first_child.data_ptr(), self.n_child.data_ptr(), self.parent.data_ptr(),
-            self.root.data_ptr(), self.n_nodes.data_ptr(), self.status.data_ptr(), self.root_boards.data_ptr(),
-            self.root_keys.data_ptr(),
-        )
+        total = self.n_pages << self.page_shift
+        g, z = self.n_games, dict(device=self.device)
+        i32 = torch.int32
+        self.nodes = torch.empty((total, 4), dtype=i32, **z)   # N, Q bits, P bits, first_child
+        self.links = torch.empty((total, 2), dtype=i32, **z)   # parent, move | n_child << 16
+        self.free_ring = torch.zeros(self.n_pages, dtype=i32, **z)
+        self.pool_ctl = torch.zeros(CTL_WORDS, dtype=torch.int64, **z)
+        self.page_lists = torch.zeros((2, g, self.max_pages), dtype=i32, **z)
+        self.page_fill = torch.zeros((g, self.max_pages), dtype=i32, **z)
+        self.n_pages_game = torch.zeros(g, dtype=i32, **z)
+        self.n_pages_new = torch.zeros(g, dtype=i32, **z)
+        self.list_sel = torch.zeros(g, dtype=i32, **z)
+        self.alloc_page = torch.zeros(g, dtype=i32, **z)
+        self.alloc_off = torch.zeros(g, dtype=i32, **z)
+        self.root = torch.zeros(g, dtype=i32, **z)
+        self.n_nodes = torch.zeros(g, dtype=i32, **z)
+        self.status = torch.zeros(g, dtype=i32, **z)
+        self.root_boards = torch.zeros((g, BOARD_BYTES), dtype=torch.uint8, **z)
+        self.root_keys = torch.zeros((g, KEY_WINDOW), dtype=torch.int64, **z)
+        self._tensors = (self.nodes, self.links, self.free_ring, self.pool_ctl, self.page_lists, self.page_fill,
+                         self.n_pages_game, self.n_pages_new, self.list_sel, self.alloc_page, self.alloc_off, self.root,
+                         self.n_nodes, self.status, self.root_boards, self.root_keys)
+        self.struct = ArenaStruct(self.n_games, self.n_pages, self.page_shift, self.max_pages,
+                                  *(t.data_ptr() for t in self._tensors))
+        with torch.cuda.device(self.device):
+            check(load().ccz_mcts_pool_init(self.ref, stream_ptr(self.device)), "ccz_mcts_pool_init")
 
     @property
     def ref(self):
         return ctypes.byref(self.struct)
 
+    @property
+    def page_nodes(self) -> int:
+        return 1 << self.page_shift
+
     def bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (
-            self.visits, self.value, self.prior, self.move, self.first_child, self.n_child, self.parent,
-            self.root, self.n_nodes, self.status, self.root_boards, self.root_keys))
+        return sum(t.numel() * t.element_size() for t in self._tensors)
+
+    # ---- host-side views for tests and statistics (each call synchronises) ----------------------
+    def pool_stats(self) -> dict:
+        c = self.pool_ctl.cpu().numpy()
+        free = int(c[CTL_TAIL] - c[CTL_HEAD])
+        return {"n_pages": self.n_pages, "page_nodes": self.page_nodes, "free_pages": free,
+                "min_free_pages": int(c[CTL_MIN_FREE]), "expand_failed": int(c[CTL_EXPAND_FAILED]),
+                "trees_dropped": int(c[CTL_TREES_DROPPED])}
+
+    def node_fields(self, idx: torch.Tensor) -> dict:
+        """visits / value (fp32) / prior (fp32) / first_child / parent / move / n_child of the pool indices ``idx``."""
+        idx = idx.to(torch.int64)
+        n, l = self.nodes[idx], self.links[idx]
+        word = l[..., 1]
+        return {"visits": n[..., 0], "value": n[..., 1].contiguous().view(torch.float32),
+                "prior": n[..., 2].contiguous().view(torch.float32), "first_child": n[..., 3], "parent": l[..., 0],
+                "move": ((word & 0xFFFF) ^ 0x8000) - 0x8000, "n_child": word >> 16}
+
+    def children(self, node: int) -> dict:
+        f = self.node_fields(torch.tensor([node], device=self.device))
+        fc, nc = int(f["first_child"][0]), int(f["n_child"][0])
+        return self.node_fields(torch.arange(fc, fc + nc, device=self.device))
 
 
 def mcts_reset(a: Arena, mask: torch.Tensor | None = None) -> None:
@@ -258,11 +319,21 @@ def mcts_root_visits(a: Arena, acts, visits, counts) -> None:
               "ccz_mcts_root_visits")
 
 
-def mcts_advance(src: Arena, dst: Arena, chosen: torch.Tensor) -> None:
-    if chosen.dtype != torch.int16:
-        raise CczError("chosen must be int16")
+def mcts_advance(a: Arena, chosen: torch.Tensor) -> None:
+    if chosen.dtype != torch.int16 or chosen.numel() != a.n_games:
+        raise CczError("chosen must be int16 [n_games]")
+    with torch.cuda.device(a.device):
+        check(load().ccz_mcts_advance(a.ref, _ptr(chosen), stream_ptr(a.device)), "ccz_mcts_advance")
+
+
+def mcts_reserve(a: Arena, pages_per_game: int) -> None:
+    with torch.cuda.device(a.device):
+        check(load().ccz_mcts_reserve(a.ref, int(pages_per_game), stream_ptr(a.device)), "ccz_mcts_reserve")
+
+
+def mcts_migrate(src: Arena, dst: Arena) -> None:
     with torch.cuda.device(src.device):
-        check(load().ccz_mcts_advance(src.ref, dst.ref, _ptr(chosen), stream_ptr(src.device)), "ccz_mcts_advance")
+        check(load().ccz_mcts_migrate(src.ref, dst.ref, stream_ptr(src.device)), "ccz_mcts_migrate")
 
 
 def replay_pack(hist_boards, turn_plane, acts, probs, counts):

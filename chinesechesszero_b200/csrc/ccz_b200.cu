@@ -213,10 +213,15 @@ int check_launch(const char *what) {
 
 int check_arena(const ccz_arena *a) {
     if (!a) return fail(-1, "arena is NULL");
-    if (a->n_games <= 0 || a->node_cap <= 1) return fail(-1, "arena geometry invalid");
-    if (!a->d_visits || !a->d_value || !a->d_prior || !a->d_move || !a->d_first_child || !a->d_n_child ||
-        !a->d_parent || !a->d_root || !a->d_n_nodes || !a->d_status || !a->d_root_boards || !a->d_root_keys)
+    if (a->n_games <= 0 || a->n_pages < a->n_games || a->max_pages < 1) return fail(-1, "arena geometry invalid");
+    if (a->page_shift < 7 || a->page_shift > 16 || ((long long)a->n_pages << a->page_shift) > 0x7fffffffll)
+        return fail(-1, "arena geometry invalid: page_shift must be 7..16 and n_pages << page_shift < 2^31");
+    if (!a->d_nodes || !a->d_links || !a->d_free_ring || !a->d_pool_ctl || !a->d_page_list || !a->d_page_fill ||
+        !a->d_n_pages || !a->d_n_pages_new || !a->d_list_sel || !a->d_alloc_page || !a->d_alloc_off || !a->d_root ||
+        !a->d_n_nodes || !a->d_status || !a->d_root_boards || !a->d_root_keys)
         return fail(-1, "arena has a NULL array");
+    if (((uintptr_t)a->d_nodes & 15) || ((uintptr_t)a->d_links & 7) || ((uintptr_t)a->d_pool_ctl & 7))
+        return fail(-1, "arena node arrays must be 16-byte aligned");
     return 0;
 }
 
@@ -226,7 +231,7 @@ inline int warps_grid(int n) { return (n + ccz::MCTS_WARPS - 1) / ccz::MCTS_WARP
 
 extern "C" {
 
-int ccz_version(void) { return 100; }
+int ccz_version(void) { return 200; }
 
 const char *ccz_last_error(void) { return g_err.c_str(); }
 
@@ -295,11 +300,45 @@ int ccz_board_push(uint8_t *d_boards, const int16_t *d_move_ids, int n, uint64_t
     return check_launch("board_push_kernel");
 }
 
+int ccz_mcts_pool_init(const ccz_arena *a, ccz_stream_t s) {
+    if (int rc = check_arena(a)) return rc;
+    if (int rc = ensure_device()) return rc;
+    const int n_free = a->n_pages - a->n_games;
+    int blocks = (n_free + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1024) blocks = 1024;
+    ccz::mcts_pool_init_kernel<<<blocks, 256, 0, s>>>(*a);
+    if (int rc = check_launch("mcts_pool_init_kernel")) return rc;
+    ccz::mcts_games_init_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a);
+    return check_launch("mcts_games_init_kernel");
+}
+
 int ccz_mcts_reset(const ccz_arena *a, const uint8_t *d_mask, ccz_stream_t s) {
     if (int rc = check_arena(a)) return rc;
     if (int rc = ensure_device()) return rc;
     ccz::mcts_reset_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, d_mask);
     return check_launch("mcts_reset_kernel");
+}
+
+int ccz_mcts_reserve(const ccz_arena *a, int pages_per_game, ccz_stream_t s) {
+    if (int rc = check_arena(a)) return rc;
+    if (pages_per_game < 1) return fail(-1, "ccz_mcts_reserve: pages_per_game < 1");
+    if ((long long)a->n_games * (pages_per_game + 1) > a->n_pages || pages_per_game + 1 > a->max_pages)
+        return fail(-1, "ccz_mcts_reserve: the pool cannot hold pages_per_game + 1 pages for every game");
+    if (int rc = ensure_device()) return rc;
+    ccz::mcts_reserve_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, pages_per_game);
+    return check_launch("mcts_reserve_kernel");
+}
+
+int ccz_mcts_migrate(const ccz_arena *src, const ccz_arena *dst, ccz_stream_t s) {
+    if (int rc = check_arena(src)) return rc;
+    if (int rc = check_arena(dst)) return rc;
+    if (src->n_games != dst->n_games) return fail(-1, "ccz_mcts_migrate: n_games differs");
+    if (src->d_nodes == dst->d_nodes || src->d_pool_ctl == dst->d_pool_ctl)
+        return fail(-1, "ccz_mcts_migrate: src and dst must be distinct arenas");
+    if (int rc = ensure_device()) return rc;
+    ccz::mcts_migrate_kernel<<<warps_grid(src->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*src, *dst);
+    return check_launch("mcts_migrate_kernel");
 }
 
 int ccz_mcts_select(const ccz_arena *a, float c_puct, uint8_t *d_leaf_boards, int32_t *d_leaf_nodes,
@@ -336,16 +375,15 @@ int ccz_mcts_root_visits(const ccz_arena *a, int16_t *d_acts, int32_t *d_visits,
     return check_launch("mcts_root_visits_kernel");
 }
 
-int ccz_mcts_advance(const ccz_arena *src, const ccz_arena *dst, const int16_t *d_chosen, ccz_stream_t s) {
-    if (int rc = check_arena(src)) return rc;
-    if (int rc = check_arena(dst)) return rc;
+int ccz_mcts_advance(const ccz_arena *a, const int16_t *d_chosen, ccz_stream_t s) {
+    if (int rc = check_arena(a)) return rc;
     if (!d_chosen) return fail(-1, "ccz_mcts_advance: NULL chosen");
-    if (src->n_games != dst->n_games || src->node_cap != dst->node_cap)
-        return fail(-1, "ccz_mcts_advance: src/dst geometry differs");
-    if (src->d_visits == dst->d_visits) return fail(-1, "ccz_mcts_advance: src and dst must be distinct");
     if (int rc = ensure_device()) return rc;
-    ccz::mcts_advance_kernel<<<warps_grid(src->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*src, *dst, d_chosen);
-    return check_launch("mcts_advance_kernel");
+    // pop-only kernel (compaction into fresh pages), then push-only kernel (old pages back to the ring)
+    ccz::mcts_advance_compact_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, d_chosen);
+    if (int rc = check_launch("mcts_advance_compact_kernel")) return rc;
+    ccz::mcts_advance_release_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a);
+    return check_launch("mcts_advance_release_kernel");
 }
 
 int ccz_replay_pack(const uint8_t *d_hist_boards, const uint8_t *d_turn_plane, const int16_t *d_acts,

@@ -71,8 +71,10 @@ class MCTS:
         self.c_puct = c_puct
         self.n_playout = n_playout
         if node_cap is None:
-            node_cap = max(8192, min(int(n_playout) * 128 + 256, 1 << 21))
-        self._search = LockstepSearch(1, node_cap=node_cap, device=device, c_puct=float(c_puct))
+            # one game owns the whole page pool; it starts at twice the worst case of one search and doubles
+            # whenever the kept sub-tree (mcts.py:168-178 keeps it without bound) leaves less than that free
+            node_cap = max(65536, 2 * _lib.search_pages(int(n_playout), 11) << 11)
+        self._search = LockstepSearch(1, nodes_per_game=node_cap, device=device, c_puct=float(c_puct))
         from .net import BatchedEvaluator
 
         if isinstance(self._evaluator, BatchedEvaluator):
@@ -92,6 +94,7 @@ class MCTS:
         """mcts.py:131-166: n_playout playouts, then softmax(1/temp*log(visits+1e-10)) over the root
         children in generation order.  Returns (acts tuple, probs float64 array)."""
         self._sync_root(board)
+        self._search.ensure_capacity(self.n_playout, self._search.arena.pool_ctl.cpu().numpy())
         interval = max(1, self.n_playout // 100)  # progress throttle, mcts.py:148-160
         remaining = self.n_playout
         while remaining > 0:

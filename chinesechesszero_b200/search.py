@@ -21,16 +21,34 @@ from . import _lib
 
 
 class LockstepSearch:
-    def __init__(self, n_games: int, node_cap: int = 32768, device="cuda", c_puct: float = 5.0):
+    """``nodes_per_game`` is the AVERAGE node budget of a game: all trees draw pages of ``2**page_shift``
+    nodes from one pool of ``n_games * nodes_per_game`` nodes (24 B each), so a game that keeps a large
+    sub-tree (forced replies keep almost everything, mcts.py:168-178) borrows what the others do not
+    need.  The pool grows (``ensure_capacity``: a bigger pool, trees migrated) up to ``max_pool_nodes``
+    when a caller that synchronises anyway asks for it; the device-side guard ``ccz_mcts_reserve`` runs
+    before every search and, as the last resort, drops the sub-trees of the largest games -- counted in
+    ``pool_stats()['trees_dropped']`` -- so that no expansion can fail.  ``node_cap`` is the round-1
+    name of ``nodes_per_game``."""
+
+    def __init__(self, n_games: int, nodes_per_game: int | None = None, device="cuda", c_puct: float = 5.0,
+                 page_shift: int = 11, max_pool_nodes: int | None = None, node_cap: int | None = None,
+                 max_pages_per_game: int | None = None):
         self.n_games = int(n_games)
-        self.node_cap = int(node_cap)
+        if nodes_per_game is None:
+            nodes_per_game = node_cap if node_cap is not None else 65536
+        self.nodes_per_game = int(nodes_per_game)
+        self.page_shift = int(page_shift)
         self.device = torch.device(device)
         self.c_puct = float(c_puct)
+        page = 1 << self.page_shift
+        hard = ((1 << 31) - 1) >> self.page_shift  # pool indices are int32
+        self.max_pool_pages = hard if max_pool_nodes is None else max(self.n_games, min(hard, int(max_pool_nodes) // page))
+        n_pages = min(self.max_pool_pages, max(self.n_games, -(-self.n_games * self.nodes_per_game // page)))
+        self._max_pages_per_game = max_pages_per_game
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().ccz_init(), "ccz_init")
-        # two arenas: advance() compacts the kept sub-tree from one into the other
-        self._arenas = [_lib.Arena(n_games, node_cap, self.device), _lib.Arena(n_games, node_cap, self.device)]
-        self._cur = 0
+        self._arena = _lib.Arena(self.n_games, n_pages, self.page_shift, self._game_pages(n_pages), self.device)
+        self.pool_grown = 0
         self._graphs = None
         self._graph_evaluator = None
         g, dev = self.n_games, self.device
@@ -43,12 +61,21 @@ class LockstepSearch:
         self.root_acts = torch.zeros((g, _lib.MAX_MOVES), dtype=torch.int16, device=dev)
         self.root_visit_counts = torch.zeros((g, _lib.MAX_MOVES), dtype=torch.int32, device=dev)
         self.root_counts = torch.zeros((g,), dtype=torch.int16, device=dev)
-        self.reset()
+
+    def _game_pages(self, n_pages: int) -> int:
+        """Page-list capacity of one game: the whole pool for small pools, 8192 pages (16.8 M nodes) otherwise."""
+        if self._max_pages_per_game is not None:
+            return int(self._max_pages_per_game)
+        return max(2, min(n_pages, 8192))
 
     # ------------------------------------------------------------------------------------
     @property
     def arena(self) -> _lib.Arena:
-        return self._arenas[self._cur]
+        return self._arena
+
+    @property
+    def node_cap(self) -> int:
+        return self.nodes_per_game
 
     @property
     def root_boards(self) -> torch.Tensor:
@@ -71,6 +98,54 @@ class LockstepSearch:
         a.root_boards.copy_(rec)
         a.root_keys.copy_(_lib.board_keys_init(a.root_boards))
 
+    # ---- pool capacity ---------------------------------------------------------------------
+    def search_pages(self, n_playout: int) -> int:
+        return _lib.search_pages(n_playout, self.page_shift)
+
+    def _grow(self, n_pages: int) -> bool:
+        """Replace the pool by one of ``n_pages`` pages and move every tree over (ccz_mcts_migrate)."""
+        n_pages = min(int(n_pages), self.max_pool_pages)
+        old = self._arena
+        if n_pages <= old.n_pages:
+            return False
+        need = (n_pages << self.page_shift) * _lib.NODE_BYTES + (64 << 20)
+        if torch.cuda.mem_get_info(self.device)[0] < need:
+            return False
+        new = _lib.Arena(self.n_games, n_pages, self.page_shift, self._game_pages(n_pages), self.device)
+        _lib.mcts_migrate(old, new)
+        self._arena = new
+        self.pool_grown += 1
+        if self._graphs is not None:  # captured graphs hold the old pool's pointers
+            torch.cuda.current_stream(self.device).synchronize()
+            self._graphs = {}
+        return True
+
+    def ensure_capacity(self, n_playout: int, ctl: np.ndarray | None = None) -> None:
+        """Make room for a search of ``n_playout`` playouts in every game.  Geometry first (the pool must
+        hold the worst case of a fresh tree per game); then, if ``ctl`` (a host copy of ``arena.pool_ctl``
+        taken after the last advance) shows fewer free pages than the worst case, the pool doubles.  Callers
+        that never synchronise skip this and rely on the guard in ``run``."""
+        w = self.search_pages(n_playout)
+        floor = self.n_games * (w + 1)
+        if self.arena.n_pages < floor or self.arena.max_pages < w + 1:
+            ok = floor <= self.max_pool_pages and self._grow(min(max(floor, 2 * self.arena.n_pages), self.max_pool_pages))
+            if not ok or self.arena.max_pages < w + 1:
+                raise _lib.CczError(
+                    f"MCTS pool too small: {self.n_games} games x {n_playout} playouts need at least {floor} pages of "
+                    f"{1 << self.page_shift} nodes ({w + 1} per game), the pool has {self.arena.n_pages} "
+                    f"(raise nodes_per_game / max_pool_nodes)")
+        if ctl is not None:
+            free = int(ctl[_lib.CTL_TAIL] - ctl[_lib.CTL_HEAD])
+            if free < self.n_games * w:
+                used = self.arena.n_pages - free
+                self._grow(max(2 * self.arena.n_pages, used + self.n_games * w))
+
+    def pool_stats(self) -> dict:
+        st = self.arena.pool_stats()
+        st["pool_grown"] = self.pool_grown
+        st["pool_bytes"] = (self.arena.n_pages << self.page_shift) * _lib.NODE_BYTES
+        return st
+
     # ------------------------------------------------------------------------------------
     def select_and_encode(self, planes: bool = True) -> None:
         a = self.arena
@@ -91,9 +166,14 @@ class LockstepSearch:
         self.expand_backup(policy, kind, values)
 
     def run(self, evaluator, n_playout: int) -> None:
+        if n_playout <= 0:
+            return
+        self.ensure_capacity(n_playout)  # geometry only: no synchronisation
+        # device-side guard: after it no expansion of this search can fail (see ccz_mcts_reserve)
+        _lib.mcts_reserve(self.arena, self.search_pages(n_playout))
         if self._graphs is not None and self._graph_evaluator is evaluator and n_playout > 0:
             done = 0
-            graph = self._graphs.get(self._cur)
+            graph = self._graphs.get(0)
             if graph is None:
                 # the first playout of this run doubles as the eager warm-up (lazy inits, cuDNN plans);
                 # capture itself records the launches without executing them
@@ -103,7 +183,7 @@ class LockstepSearch:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     self.step(evaluator)
-                self._graphs[self._cur] = graph
+                self._graphs[0] = graph
             for _ in range(n_playout - done):
                 graph.replay()
             return
@@ -112,8 +192,8 @@ class LockstepSearch:
 
     # ---- CUDA graphs: one captured lockstep step per arena side --------------------------------
     def enable_graphs(self, evaluator) -> None:
-        """Capture K3 -> K1 -> evaluator -> K4/K5 into a CUDA graph (one per ping-pong arena, captured
-        on first use) and replay it in ``run``.  The evaluator must be capture-safe and static
+        """Capture K3 -> K1 -> evaluator -> K4/K5 into a CUDA graph (captured on first use, again after
+        the pool has grown) and replay it in ``run``.  The evaluator must be capture-safe and static
         (device-only work, no host synchronisation), e.g. ``net.BatchedEvaluator``.  It removes the
         per-step launch overhead (~170 launches), which matters when the leaf batch is small."""
         self._graphs = {}
@@ -136,19 +216,21 @@ class LockstepSearch:
         ch = torch.as_tensor(chosen, dtype=torch.int16).to(self.device).contiguous()
         if ch.shape != (self.n_games,):
             raise ValueError("chosen must have one entry per game")
-        src, dst = self._arenas[self._cur], self._arenas[1 - self._cur]
-        _lib.mcts_advance(src, dst, ch)
-        self._cur = 1 - self._cur
+        _lib.mcts_advance(self.arena, ch)
 
     def check_status(self) -> None:
+        """Raises when a leaf was left unexpanded (pool exhausted in spite of the guard) -- the only event
+        that takes a search off the reference's sequence without restarting it.  Dropped sub-trees are
+        reported by ``pool_stats()`` and the per-game status bits, not raised."""
         st = self.arena.status
-        if bool((st != 0).any()):
-            bad = torch.nonzero(st).flatten()[:8].tolist()
+        if bool(((st & _lib.STATUS_EXPAND_FAILED) != 0).any()):
+            bad = torch.nonzero(st & _lib.STATUS_EXPAND_FAILED).flatten()[:8].tolist()
             raise _lib.CczError(
-                f"MCTS arena overflow (node_cap={self.node_cap}) in games {bad}: results invalid, raise node_cap")
+                f"MCTS page pool exhausted ({self.arena.n_pages} pages of {1 << self.page_shift} nodes) in games {bad}: "
+                "leaves were left unexpanded, raise nodes_per_game / max_pool_nodes")
 
     def memory_bytes(self) -> int:
-        return sum(a.bytes() for a in self._arenas)
+        return self.arena.bytes()
 
 
 def visit_softmax(visits: np.ndarray, temp: float) -> np.ndarray:

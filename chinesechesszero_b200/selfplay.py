@@ -54,20 +54,26 @@ class SelfPlayEngine:
     def __init__(self, evaluator: Callable, n_games: int, n_playout: int = 400, c_puct: float = 5.0,
                  temp: float = 1.0, node_cap: int | None = None, device="cuda", seed: int = 0,
                  deterministic: bool = False, max_game_moves: int | None = None, use_graphs: bool = False,
-                 resident_ring: int = 16):
+                 resident_ring: int = 16, nodes_per_game: int | None = None, page_shift: int = 11,
+                 max_pool_nodes: int | None = None):
         self.evaluator = evaluator
         self.n_games, self.n_playout = int(n_games), int(n_playout)
         self.temp = float(temp)
         self.deterministic = bool(deterministic)
         self.max_game_moves = max_game_moves
         self.resident_ring = int(resident_ring)
-        if node_cap is None:
-            # Per move a tree gains n_playout expansions of ~41 (at most 119) children on top of the
-            # sub-tree kept by the last advance().  With kept fraction f the steady state is about
-            # 41*n_playout/(1-f) nodes: 4x the per-move growth covers f <= 0.75 (a random-init net keeps
-            # ~1/40).  Strongly peaked nets want more (22 B/node/arena; overflow raises, never truncates).
-            node_cap = max(4096, int(self.n_playout * 41 * 4))
-        self.search = LockstepSearch(n_games, node_cap=node_cap, device=device, c_puct=c_puct)
+        if nodes_per_game is None:
+            nodes_per_game = node_cap  # round-1 name
+        if nodes_per_game is None:
+            # AVERAGE budget per game of the shared page pool (search.LockstepSearch): per move a tree gains
+            # n_playout expansions of ~41 (at most 119) children on top of the sub-tree kept by the last advance().
+            # Measured with a near-uniform policy at 400 playouts: median live tree 23k nodes, p99 35k, and a
+            # tail of forced-reply sequences beyond 65k -- which a pool absorbs because only the
+            # SUM over the games has to fit.  6x the mean growth per move leaves the worst-case reservation of
+            # every game (119 children per playout) on top of a 2x mean live tree; the pool doubles on demand.
+            nodes_per_game = max(4096, int(self.n_playout * 41 * 6))
+        self.search = LockstepSearch(n_games, nodes_per_game=nodes_per_game, device=device, c_puct=c_puct,
+                                     page_shift=page_shift, max_pool_nodes=max_pool_nodes)
         if use_graphs:  # replay the lockstep step from CUDA graphs (capture-safe evaluators only)
             self.search.enable_graphs(evaluator)
         self.rng = np.random.default_rng(seed)
@@ -88,6 +94,8 @@ class SelfPlayEngine:
         self._h_boards = torch.empty((g, _lib.BOARD_BYTES), dtype=torch.uint8, **pin)
         self._h_flags = torch.empty((g,), dtype=torch.uint8, **pin)
         self._h_chosen = torch.empty((g,), dtype=torch.int16, **pin)
+        self._h_ctl = torch.zeros((_lib.CTL_WORDS,), dtype=torch.int64, **pin)
+        self._ctl_valid = False
         self._d_chosen = torch.empty((g,), dtype=torch.int16, device=self.device)
         self._d_mask = torch.empty((g,), dtype=torch.uint8, device=self.device)
         self._h_mask = torch.empty((g,), dtype=torch.uint8, **pin)
@@ -96,6 +104,7 @@ class SelfPlayEngine:
                           torch.empty((g,), dtype=torch.uint8, device=self.device), None)
         self.total_moves = 0
         self.total_games = 0
+        self.resident_backlog: list[dict] = []   # drained rings of the resident path, oldest first
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -108,6 +117,9 @@ class SelfPlayEngine:
     def play_move(self) -> list[GameRecord]:
         """One lockstep move in every slot; returns the games that finished with it."""
         s = self.search
+        # the pool counters read back with the last move tell whether this search fits: grow the pool (trees
+        # migrate, nothing is lost) instead of letting the device-side guard drop sub-trees
+        s.ensure_capacity(self.n_playout, self._h_ctl.numpy() if self._ctl_valid else None)
         s.run(self.evaluator, self.n_playout)
         acts_d, visits_d, counts_d = s.root_visits()
         self._h_acts.copy_(acts_d, non_blocking=True)
@@ -115,7 +127,6 @@ class SelfPlayEngine:
         self._h_counts.copy_(counts_d, non_blocking=True)
         self._h_boards.copy_(s.root_boards, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        s.check_status()
         self.d2h_bytes += sum(t.numel() * t.element_size() for t in
                               (self._h_acts, self._h_visits, self._h_counts, self._h_boards))
         acts_np, visits_np = self._h_acts.numpy(), self._h_visits.numpy()
@@ -157,8 +168,10 @@ class SelfPlayEngine:
         _lib.movegen_encode(s.root_boards, planes=False, out=self._flag_out)
         self._h_flags.copy_(self._flag_out[2], non_blocking=True)
         self._h_boards.copy_(s.root_boards, non_blocking=True)
+        self._h_ctl.copy_(s.arena.pool_ctl, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        self.d2h_bytes += self._h_flags.numel() + self._h_boards.numel()
+        self._ctl_valid = True
+        self.d2h_bytes += self._h_flags.numel() + self._h_boards.numel() + self._h_ctl.numel() * 8
         flags = self._h_flags.numpy()
         over = (flags & (_lib.FLAG_TIE_MASK | _lib.FLAG_NOMOVES)) != 0
         if self.max_game_moves is not None:
@@ -270,7 +283,9 @@ class SelfPlayEngine:
         r["ring_over"][slot].copy_(self._d_mask)
         r["ring_flags"][slot].copy_(self._flag_out[2])
         r["head"] = (slot + 1) % r["ring"]
-        r["filled"] = min(r["filled"] + 1, r["ring"])
+        r["filled"] += 1
+        if r["filled"] == r["ring"]:  # never overwrite samples: a full ring goes to the host backlog
+            self.resident_backlog.append(self.drain_resident())
         s.reset(self._d_mask)
         r["move_count"] = torch.where(over, torch.zeros_like(mc), mc)
         r["finished"] += over.sum()
@@ -288,6 +303,11 @@ class SelfPlayEngine:
                for k in ("boards", "acts", "pi", "counts", "moves", "over", "flags")}
         r["filled"] = 0
         return out
+
+    def pool_events(self) -> dict:
+        """Cumulative pool counters (synchronises): ``trees_dropped`` and ``expand_failed`` are 0 unless
+        the pool could not grow any further; see ``search.LockstepSearch``."""
+        return self.search.pool_stats()
 
     def play(self, n_moves: int) -> list[GameRecord]:
         out = []

@@ -48,30 +48,69 @@ typedef struct CUstream_st *ccz_stream_t; /* == cudaStream_t */
 #define CCZ_FLAG_SIXTY 16       /* board.is_sixty_moves() */
 #define CCZ_FLAG_TIE_MASK (CCZ_FLAG_INSUFFICIENT | CCZ_FLAG_FOURFOLD | CCZ_FLAG_SIXTY)
 
-/* per-game status bits (ccz_arena.d_status) */
-#define CCZ_STATUS_NODE_OVERFLOW 1
+/* per-game status bits (ccz_arena.d_status); sticky until the slot is reset for a new game */
+#define CCZ_STATUS_EXPAND_FAILED 1 /* a leaf stayed unexpanded: the page pool was exhausted (last resort) */
+#define CCZ_STATUS_TREE_DROPPED 2  /* the kept sub-tree was dropped to free pool pages (reserve / advance) */
+#define CCZ_STATUS_NODE_OVERFLOW CCZ_STATUS_EXPAND_FAILED /* round-1 name */
 
 /* kinds of policy input accepted by ccz_mcts_expand_backup */
 #define CCZ_POLICY_PROBS 0  /* fp32 probabilities, gathered as-is (bit-exact path) */
 #define CCZ_POLICY_LOGITS 1 /* fp32 logits; softmax over all 2086 fused into the gather */
 
-/* Flat MCTS arena: `n_games` independent trees, each owning `node_cap` node slots.  Node i of
- * game g lives at index g*node_cap + i of every d_node_* array; the children of a node are the
- * contiguous slots [first_child, first_child + n_child) in cchess generation order (the
- * reference's insertion-ordered dict, mcts.py:37-39). */
+/* special values of d_chosen[g] in ccz_mcts_advance */
+#define CCZ_ADVANCE_NEW_GAME (-1)  /* start position, fresh root */
+#define CCZ_ADVANCE_DROP_TREE (-2) /* keep the position, fresh root */
+
+/* A tree node is two records so that one 16-byte load per lane brings everything PUCT needs of a
+ * child (N, Q, P) plus the link to ITS children, and the cold fields stay out of that stream. */
+typedef struct {
+    int32_t visits;      /* N   (mcts.py:16) */
+    float value;         /* Q   (mcts.py:15), fp32 incremental mean */
+    float prior;         /* P   (mcts.py:17) */
+    int32_t first_child; /* pool index of the first child, -1 if none */
+} ccz_node;              /* 16 B */
+typedef struct {
+    int32_t parent;  /* pool index, -1 for the root */
+    int16_t move;    /* action id that leads to this node */
+    int16_t n_child; /* 0 = leaf (mcts.py:19-23) */
+} ccz_link;          /* 8 B */
+
+/* control words of the page pool (ccz_arena.d_pool_ctl, int64 each) */
+#define CCZ_CTL_HEAD 0          /* pages popped from the free ring so far */
+#define CCZ_CTL_TAIL 1          /* pages pushed to the free ring so far; free = TAIL - HEAD */
+#define CCZ_CTL_EXPAND_FAILED 2 /* cumulative count of leaves left unexpanded (never cleared by reset / advance) */
+#define CCZ_CTL_TREES_DROPPED 3 /* cumulative count of sub-trees dropped (never cleared by reset / advance) */
+#define CCZ_CTL_MIN_FREE 4      /* low-water mark of free pages */
+#define CCZ_CTL_WORDS 8
+
+/* Pooled MCTS arena: `n_games` independent trees whose nodes come from ONE pool of `n_pages` pages
+ * of 2^page_shift nodes (the reference's tree, mcts.py:31-39, has no capacity: a game that keeps a
+ * large sub-tree borrows pages that games with small trees do not need).  A node is addressed by
+ * its pool index; the children of a node are the contiguous slots [first_child, first_child +
+ * n_child) -- always inside one page -- in cchess generation order (the reference's
+ * insertion-ordered dict, mcts.py:37-39).  Each game bump-allocates child runs in its current page
+ * and pops a new page from the free ring when a run does not fit; ccz_mcts_advance compacts the
+ * kept sub-tree into fresh pages and returns the old ones.  The page lists ping-pong between the
+ * two halves of d_page_list (d_list_sel[g] names the live half). */
 typedef struct {
     int32_t n_games;
-    int32_t node_cap;
-    int32_t *d_visits;      /* N   (mcts.py:16) */
-    float *d_value;         /* Q   (mcts.py:15), fp32 incremental mean */
-    float *d_prior;         /* P   (mcts.py:17) */
-    int16_t *d_move;        /* action id that leads to this node */
-    int32_t *d_first_child; /* local index of the first child, -1 if none */
-    int16_t *d_n_child;     /* 0 = leaf (mcts.py:19-23) */
-    int32_t *d_parent;      /* local index, -1 for the root */
-    int32_t *d_root;        /* [n_games] local index of the root node */
-    int32_t *d_n_nodes;     /* [n_games] bump pointer */
-    int32_t *d_status;      /* [n_games] CCZ_STATUS_* bits, sticky */
+    int32_t n_pages;    /* pool size in pages; n_pages << page_shift < 2^31 */
+    int32_t page_shift; /* 7..16: a page must hold one child run (<= 128 nodes) */
+    int32_t max_pages;  /* page-list capacity of one game */
+    ccz_node *d_nodes;  /* [n_pages << page_shift] */
+    ccz_link *d_links;  /* [n_pages << page_shift] */
+    int32_t *d_free_ring;   /* [n_pages] page ids; live entries are HEAD .. TAIL-1 (mod n_pages) */
+    int64_t *d_pool_ctl;    /* [CCZ_CTL_WORDS] */
+    int32_t *d_page_list;   /* [2, n_games, max_pages] pages owned by each game */
+    int32_t *d_page_fill;   /* [n_games, max_pages] scratch of ccz_mcts_advance: nodes used in each new page */
+    int32_t *d_n_pages;     /* [n_games] entries of the live page list */
+    int32_t *d_n_pages_new; /* [n_games] scratch of ccz_mcts_advance */
+    int32_t *d_list_sel;    /* [n_games] 0 / 1: live half of d_page_list */
+    int32_t *d_alloc_page;  /* [n_games] page the next child run is carved from */
+    int32_t *d_alloc_off;   /* [n_games] first unused slot of that page */
+    int32_t *d_root;        /* [n_games] pool index of the root node */
+    int32_t *d_n_nodes;     /* [n_games] live nodes of the tree */
+    int32_t *d_status;      /* [n_games] CCZ_STATUS_* bits */
     uint8_t *d_root_boards; /* [n_games, 96] position at the root */
     uint64_t *d_root_keys;  /* [n_games, 128] position keys since the last capture; entry
                                `clock` is the root position itself */
@@ -107,12 +146,29 @@ int ccz_board_push(uint8_t *d_boards, const int16_t *d_move_ids, int n, uint64_t
  * the record, earlier entries = a sentinel that matches nothing). */
 int ccz_board_keys_init(const uint8_t *d_boards, int n, uint64_t *d_keys, ccz_stream_t s);
 
-/* Reset trees to a single unvisited root (Node(None, 1.0), mcts.py:94) over the start position
- * (game.py:148).  d_mask NULL = every game, else only games with d_mask[g] != 0 (slot refill). */
+/* First use of an arena: builds the free ring, hands every game one page and resets every tree to a
+ * single unvisited root (Node(None, 1.0), mcts.py:94) over the start position (game.py:148).  The
+ * cumulative counters in d_pool_ctl start at zero.  Needs n_pages >= n_games. */
+int ccz_mcts_pool_init(const ccz_arena *a, ccz_stream_t s);
+
+/* Reset trees to a single unvisited root over the start position; the pages of the old tree go
+ * back to the pool.  d_mask NULL = every game, else only games with d_mask[g] != 0 (slot refill). */
 int ccz_mcts_reset(const ccz_arena *a, const uint8_t *d_mask /*[n_games] or NULL*/, ccz_stream_t s);
 
+/* Guarantee, before a search, that every game can grow by `pages_per_game` pages: if the free ring
+ * holds fewer than n_games * pages_per_game pages, or a game's page list would overflow, the trees
+ * of the games that hold more than their share (n_pages / n_games - pages_per_game) are dropped
+ * (fresh root on the same position, CCZ_STATUS_TREE_DROPPED, CCZ_CTL_TREES_DROPPED += 1).  After
+ * it no expansion of the following pages_per_game-page search can fail.  Callers that may
+ * synchronise grow the pool instead (ccz_mcts_migrate) and never reach the dropping branch. */
+int ccz_mcts_reserve(const ccz_arena *a, int pages_per_game, ccz_stream_t s);
+
+/* Move every tree, root position and key window into another (larger) arena of the same n_games;
+ * dst must have been initialised with ccz_mcts_pool_init.  Cumulative counters carry over. */
+int ccz_mcts_migrate(const ccz_arena *src, const ccz_arena *dst, ccz_stream_t s);
+
 /* One selection pass per game: descend by PUCT from the root to a leaf, replaying the moves.
- * Writes the leaf position and the leaf's local node index. */
+ * Writes the leaf position and the leaf's pool index. */
 int ccz_mcts_select(const ccz_arena *a, float c_puct, uint8_t *d_leaf_boards /*[n,96]*/,
                     int32_t *d_leaf_nodes /*[n]*/, ccz_stream_t s);
 
@@ -127,12 +183,13 @@ int ccz_mcts_expand_backup(const ccz_arena *a, const int32_t *d_leaf_nodes, cons
 int ccz_mcts_root_visits(const ccz_arena *a, int16_t *d_acts /*[n,128]*/,
                          int32_t *d_visits /*[n,128]*/, int16_t *d_counts /*[n]*/, ccz_stream_t s);
 
-/* Play d_chosen[g] in game g: the chosen child's sub-tree is compacted into `dst` (tree reuse),
- * the root board and key window advance.  d_chosen[g] == -1 resets game g to the start position
- * with a fresh root; -2 keeps the position but drops the tree.  src and dst must be distinct
- * arenas with the same geometry. */
-int ccz_mcts_advance(const ccz_arena *src, const ccz_arena *dst, const int16_t *d_chosen,
-                     ccz_stream_t s);
+/* Play d_chosen[g] in game g (MCTS.update_with_move, mcts.py:168-178): the chosen child's sub-tree
+ * is compacted breadth-first into fresh pages (tree reuse; visit counts and Q carry over), the
+ * pages of the rest go back to the pool, the root board and key window advance.
+ * CCZ_ADVANCE_NEW_GAME resets game g to the start position with a fresh root,
+ * CCZ_ADVANCE_DROP_TREE keeps the position but drops the tree; an id that is not a root child
+ * gives a fresh root as in the reference (mcts.py:177-178). */
+int ccz_mcts_advance(const ccz_arena *a, const int16_t *d_chosen, ccz_stream_t s);
 
 /* Replay densification (collect.py:64-131): for each of n samples scatter the sparse visit
  * distribution into a dense float64 row of 2086 and its file-mirrored twin, and write the

@@ -58,7 +58,7 @@ def test_decode_board_matches_oracle():
 def test_struct_layout_matches_header():
     from chinesechesszero_b200 import _lib
 
-    assert ctypes.sizeof(_lib.ArenaStruct) == 8 + 12 * 8
+    assert ctypes.sizeof(_lib.ArenaStruct) == 16 + 16 * 8
 
 
 def test_header_is_valid_c_and_matches_ctypes_struct(tmp_path):
@@ -70,14 +70,15 @@ def test_header_is_valid_c_and_matches_ctypes_struct(tmp_path):
 
     src = tmp_path / "t.c"
     src.write_text('#include <stdio.h>\n#include "ccz_b200.h"\n'
-                   'int main(void){printf("%zu %d %d %d\\n", sizeof(ccz_arena), CCZ_BOARD_BYTES, CCZ_N_ACTIONS, '
-                   'CCZ_FLAG_TIE_MASK);return 0;}\n')
+                   'int main(void){printf("%zu %d %d %d %zu %zu\\n", sizeof(ccz_arena), CCZ_BOARD_BYTES, CCZ_N_ACTIONS, '
+                   'CCZ_FLAG_TIE_MASK, sizeof(ccz_node), sizeof(ccz_link));return 0;}\n')
     exe = tmp_path / "t"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
                    check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == ctypes.sizeof(_lib.ArenaStruct)
-    assert [int(x) for x in out[1:]] == [_lib.BOARD_BYTES, _lib.N_ACTIONS, _lib.FLAG_TIE_MASK]
+    assert [int(x) for x in out[1:]] == [_lib.BOARD_BYTES, _lib.N_ACTIONS, _lib.FLAG_TIE_MASK, 16, 8]
+    assert _lib.NODE_BYTES == 24
 
 
 def test_conv_work_plan_covers_every_tile_and_channel_exactly_once():

@@ -33,14 +33,24 @@ def test_bad_arguments_return_status_and_message():
     assert lib.ccz_movegen_encode(None, 0, None, None, None, None, s) == 0
     with pytest.raises(_lib.CczError):
         _lib.movegen_encode(torch.zeros((2, 96), dtype=torch.uint8))  # host tensor: device pointers only
-    a = _lib.Arena(2, 64)
+    a = _lib.Arena(2, 8, page_shift=7)
     bad = _lib.ArenaStruct.from_buffer_copy(a.struct)
-    bad.d_value = None
+    bad.d_links = None
     assert lib.ccz_mcts_reset(ctypes.byref(bad), None, s) < 0 and b"NULL" in lib.ccz_last_error()
-    b2 = _lib.Arena(3, 64)
+    bad = _lib.ArenaStruct.from_buffer_copy(a.struct)
+    bad.page_shift = 6  # a page must hold one child run
+    assert lib.ccz_mcts_reset(ctypes.byref(bad), None, s) < 0 and b"geometry" in lib.ccz_last_error()
+    bad = _lib.ArenaStruct.from_buffer_copy(a.struct)
+    bad.n_pages = 1  # fewer pages than games
+    assert lib.ccz_mcts_pool_init(ctypes.byref(bad), s) < 0 and b"geometry" in lib.ccz_last_error()
+    b2 = _lib.Arena(3, 8, page_shift=7)
     chosen = torch.zeros(2, dtype=torch.int16, device="cuda")
-    assert lib.ccz_mcts_advance(a.ref, b2.ref, chosen.data_ptr(), s) < 0 and b"geometry" in lib.ccz_last_error()
-    assert lib.ccz_mcts_advance(a.ref, a.ref, chosen.data_ptr(), s) < 0 and b"distinct" in lib.ccz_last_error()
+    assert lib.ccz_mcts_migrate(a.ref, b2.ref, s) < 0 and b"n_games" in lib.ccz_last_error()
+    assert lib.ccz_mcts_migrate(a.ref, a.ref, s) < 0 and b"distinct" in lib.ccz_last_error()
+    assert lib.ccz_mcts_advance(a.ref, None, s) < 0 and b"NULL" in lib.ccz_last_error()
+    assert lib.ccz_mcts_reserve(a.ref, 0, s) < 0 and lib.ccz_mcts_reserve(a.ref, 4, s) < 0  # 2 games x 5 pages > 8
+    assert b"pool cannot hold" in lib.ccz_last_error()
+    assert lib.ccz_mcts_reserve(a.ref, 3, s) == 0
     assert lib.ccz_mcts_expand_backup(a.ref, chosen.data_ptr(), chosen.data_ptr(), 7, chosen.data_ptr(),
                                       chosen.data_ptr(), chosen.data_ptr(), chosen.data_ptr(), s) < 0
     torch.cuda.synchronize()

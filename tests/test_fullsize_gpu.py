@@ -46,12 +46,13 @@ def test_movegen_encode_one_million_positions_properties():
 def test_lockstep_search_4096_games_tree_invariants():
     from chinesechesszero_b200 import _lib
     from chinesechesszero_b200.search import LockstepSearch
+    from tests.arena_util import pool_accounting, walk_tree
 
     G, P = 4096, 64
     torch.manual_seed(0)
     logits = torch.randn(G, 2086, device="cuda")
     values = torch.tanh(torch.randn(G, device="cuda") * 0.5)
-    s = LockstepSearch(G, node_cap=8192)
+    s = LockstepSearch(G, nodes_per_game=8192)
     ev = lambda planes, boards: (logits, _lib.POLICY_LOGITS, values)
     s.run(ev, P)
     s.check_status()
@@ -59,35 +60,44 @@ def test_lockstep_search_4096_games_tree_invariants():
     acts, visits, counts = s.root_visits()
     # first search of a game: the root is expanded by playout 1, children receive P-1 visits (mcts.py:94, B.4)
     assert bool((visits.sum(1) == P - 1).all()) and bool((counts == 44).all())
-    root = a.root.to(torch.int64) + torch.arange(G, device="cuda") * a.node_cap
-    assert bool((a.visits[root] == P).all())
-    assert bool((a.value.abs() <= 1.0 + 1e-6).all())
-    # every child run is inside the arena and points back to its parent
+    root = a.root.to(torch.int64)
+    assert bool((a.nodes[root, 0] == P).all())
     nn = a.n_nodes.to(torch.int64)
-    assert int(nn.max()) <= a.node_cap and int(nn.min()) >= 45
-    g0 = 17
-    base = g0 * a.node_cap
-    n0 = int(nn[g0])
-    fc = a.first_child[base:base + n0].cpu().numpy()
-    nc = a.n_child[base:base + n0].cpu().numpy()
-    par = a.parent[base:base + n0].cpu().numpy()
-    vis = a.visits[base:base + n0].cpu().numpy()
-    for i in np.nonzero(nc > 0)[0]:
-        kids = np.arange(fc[i], fc[i] + nc[i])
-        assert (par[kids] == i).all()
-        assert vis[i] == vis[kids].sum() + 1      # N(node) = sum N(children) + its own expansion visit
+    assert int(nn.min()) >= 45 and int(nn.max()) <= 1 + P * 119
+    # whole trees: child runs inside one owned page, parent links, N(node) = 1 + sum N(children), node counts
+    for g0 in (0, 17, 4095):
+        t = walk_tree(a, g0)
+        assert np.abs(t["value"]).max() <= 1.0 + 1e-6
+    pool_accounting(a)
     # advancing every game keeps exactly the chosen sub-tree
     choice = visits.argmax(1, keepdim=True)
     chosen = acts.gather(1, choice.long()).view(-1).contiguous()
     kept_visits = visits.gather(1, choice.long()).view(-1)
+    before = walk_tree(a, 17, check=False)
     s.advance(chosen)
-    b = s.arena
-    root2 = b.root.to(torch.int64) + torch.arange(G, device="cuda") * b.node_cap
-    assert bool((b.visits[root2] == kept_visits).all()) and bool((b.parent[root2] == -1).all())
+    root2 = a.root.to(torch.int64)
+    assert bool((a.nodes[root2, 0] == kept_visits).all()) and bool((a.links[root2, 0] == -1).all())
+    after = walk_tree(a, 17)
+    # the kept sub-tree is the chosen child's, node for node in breadth-first order
+    kid = int(np.nonzero((before["depth"] == 1) & (before["move"] == int(chosen[17])))[0][0])
+    sub = [kid]
+    index_pos = {int(ix): i for i, ix in enumerate(before["index"])}
+    h = 0
+    while h < len(sub):
+        i = sub[h]
+        fc, nc = int(before["first_child"][i]), int(before["n_child"][i])
+        sub.extend(index_pos[fc + k] for k in range(nc))
+        h += 1
+    for key in ("visits", "value", "prior", "move", "n_child"):
+        assert np.array_equal(before[key][sub], after[key]), key
+    st = pool_accounting(a)
+    assert st["expand_failed"] == 0 and st["trees_dropped"] == 0
     s.run(ev, 8)
     s.check_status()
     _, v2, _ = s.root_visits()
     assert bool((v2.sum(1) == torch.clamp(kept_visits - 1, min=0) + 8).all())
+    walk_tree(a, 17)
+    pool_accounting(a)
 
 
 @pytest.mark.parametrize("tap", [(1, 1), (0, 0), (2, 2), (0, 2)])

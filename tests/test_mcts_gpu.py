@@ -34,12 +34,10 @@ def fake_evaluator(kind):
 
 def root_children(search, g):
     a = search.arena
-    base = g * a.node_cap
     root = int(a.root[g])
-    fc, nc = int(a.first_child[base + root]), int(a.n_child[base + root])
-    sl = slice(base + fc, base + fc + nc)
-    return (a.move[sl].cpu().numpy().tolist(), a.visits[sl].cpu().numpy().tolist(),
-            a.value[sl].cpu().numpy().view(np.uint32).tolist(), int(a.visits[base + root]))
+    kids = a.children(root)
+    return (kids["move"].cpu().numpy().tolist(), kids["visits"].cpu().numpy().tolist(),
+            kids["value"].cpu().numpy().view(np.uint32).tolist(), int(a.nodes[root, 0]))
 
 
 def make_search(sc, n_games):
@@ -151,16 +149,41 @@ def test_logits_policy_matches_probs_policy():
         s = LockstepSearch(n_games=G, node_cap=4096)
         s.step(lambda planes, boards: (pol, kind, vals))
         a = s.arena
-        priors.append(torch.stack([a.prior[g * a.node_cap + 1: g * a.node_cap + 45] for g in range(G)]).cpu())
+        priors.append(torch.stack([a.children(int(a.root[g]))["prior"] for g in range(G)]).cpu())
+        assert priors[-1].shape == (G, 44)
     assert torch.allclose(priors[0], priors[1], atol=1e-6, rtol=1e-5)
     assert float(priors[0].sum()) > 0
 
 
-def test_arena_overflow_is_reported():
+def test_pool_exhaustion_is_per_game_and_counted():
+    """Raw C-ABI use without the reserve guard on a pool with no spare page: the leaf whose child run does
+    not fit stays unexpanded (status bit on THAT game only, cumulative counter), every other game and the
+    next searches of the same game carry on; LockstepSearch.check_status names the game."""
     from chinesechesszero_b200 import _lib
     from chinesechesszero_b200.search import LockstepSearch
 
-    s = LockstepSearch(n_games=2, node_cap=64)
-    s.run(fake_evaluator("hash"), 5)
-    with pytest.raises(_lib.CczError):
+    s = LockstepSearch(n_games=2, nodes_per_game=256, page_shift=7)  # 4 pages of 128 nodes
+    assert s.arena.n_pages == 4
+    ev = fake_evaluator("hash")
+    # two playouts per game fit (root run of 44 + one more run in the game's own page + one popped page)
+    for _ in range(2):
+        s.step(ev)
+    assert s.pool_stats()["expand_failed"] == 0
+    for _ in range(6):  # 2 spare pages only: both games run dry within a few expansions
+        s.step(ev)
+    st = s.pool_stats()
+    assert st["expand_failed"] >= 1 and st["free_pages"] == 0 and st["min_free_pages"] == 0
+    status = s.arena.status.cpu().numpy()
+    assert (status & _lib.STATUS_EXPAND_FAILED).any()
+    with pytest.raises(_lib.CczError, match="pool exhausted"):
         s.check_status()
+    # visits stay consistent: every playout was backed up to the root even when its leaf was not expanded
+    assert [int(s.arena.nodes[int(s.arena.root[g]), 0]) for g in range(2)] == [8, 8]
+    # a new game in the slot gives the pages back and clears the sticky bit; the counter stays
+    s.reset()
+    assert int(s.arena.status.abs().sum()) == 0
+    st2 = s.pool_stats()
+    assert st2["free_pages"] == 2 and st2["expand_failed"] == st["expand_failed"]
+    s.run(ev, 2)  # through the guard: 2 playouts need 3 pages per game -> the pool grows instead of failing
+    assert s.pool_stats()["expand_failed"] == st["expand_failed"] and s.pool_grown == 1
+    s.check_status()
