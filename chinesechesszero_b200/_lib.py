@@ -24,7 +24,7 @@ FLAG_CHECK, FLAG_NOMOVES, FLAG_INSUFFICIENT, FLAG_FOURFOLD, FLAG_SIXTY = 1, 2, 4
 FLAG_TIE_MASK = FLAG_INSUFFICIENT | FLAG_FOURFOLD | FLAG_SIXTY
 STATUS_EXPAND_FAILED, STATUS_TREE_DROPPED = 1, 2
 STATUS_NODE_OVERFLOW = STATUS_EXPAND_FAILED
-ADVANCE_NEW_GAME, ADVANCE_DROP_TREE = -1, -2
+ADVANCE_NEW_GAME, ADVANCE_DROP_TREE, ADVANCE_KEEP = -1, -2, -3
 CTL_HEAD, CTL_TAIL, CTL_EXPAND_FAILED, CTL_TREES_DROPPED, CTL_MIN_FREE, CTL_WORDS = 0, 1, 2, 3, 4, 8
 NODE_BYTES = 24  # ccz_node (16) + ccz_link (8)
 MAX_CHILDREN = 119  # most legal moves of any Xiangqi position

@@ -28,7 +28,8 @@ from .selfplay import SelfPlayEngine
 class CollectPipeline:
     def __init__(self, init_model=None, n_games=4096, n_playout=PLAYOUT, c_puct=C_PUCT, data_dir=DATA_DIR,
                  states_mode="reference", seed=0, node_cap=None, max_game_moves=None, net_kwargs=None,
-                 write_h5=True, write_npy=True, rank=0, world=1):
+                 write_h5=True, write_npy=True, rank=0, world=1, gzip_level=4, h5_flush_every=None,
+                 async_writer=True, evaluator=None):
         self.temp = 1.0
         self.n_playout = n_playout
         self.c_puct = c_puct
@@ -37,6 +38,7 @@ class CollectPipeline:
         self.episode_len = 0
         self.policy_value_net = None
         self.engine = None
+        self._evaluator = evaluator  # a ready device evaluator instead of loading a model (benchmarks, tests)
         self.rank, self.world = int(rank), int(world)
         self.data_dir = data_dir if self.world == 1 else os.path.join(data_dir, f"rank{self.rank}")
         self.data_path = os.path.join(self.data_dir, "data.h5")
@@ -46,39 +48,73 @@ class CollectPipeline:
         self.max_game_moves = max_game_moves
         self.net_kwargs = net_kwargs or {}
         self.npy = replay.NpyReplayWriter(self.data_dir) if write_npy else None
-        self.h5 = h5lite.H5ReplayWriter(self.data_path) if write_h5 else None
-        # collect.py:39-45: the game counter continues from the file's ``iters`` attribute
-        self.local_games = self.h5.iters if (self.h5 is not None and self.world == 1) else 0
+        self.h5 = h5lite.H5ReplayWriter(self.data_path, gzip_level=gzip_level, flush_every=h5_flush_every) if write_h5 else None
+        # collect.py:39-45: the game counter continues from the file.  One GPU: the ``iters`` attribute.  A shard of
+        # a multi-GPU run holds every world-th game number, so its own count is the number of groups it links.
+        if self.h5 is None:
+            self.local_games = 0
+        elif self.world == 1:
+            self.local_games = self.h5.iters
+        else:
+            self.local_games = self.h5.n_groups
         self.iters = self.local_games
+        self.packer = None
+        # compression + file writes happen on a worker thread; ``async_writer=False`` keeps them inline
+        self.writer = replay.AsyncReplayWriter(self.h5, self.npy) if async_writer else None
 
     def load_model(self):
         """collect.py:47-62: load once; fall back to random init when the model cannot be loaded."""
-        if self.policy_value_net is None:
-            model_path = self.init_model if self.init_model else os.path.join(MODEL_DIR, "current_policy.pkl")
-            try:
-                self.policy_value_net = PolicyValueNet(model=model_path, **self.net_kwargs)
-            except Exception:
-                self.policy_value_net = PolicyValueNet(**self.net_kwargs)
-            self.engine = SelfPlayEngine(self.policy_value_net.evaluator(), n_games=self.n_games,
-                                         n_playout=self.n_playout, c_puct=self.c_puct, temp=self.temp,
-                                         seed=self.seed, node_cap=self.node_cap,
-                                         max_game_moves=self.max_game_moves)
+        if self.engine is None:
+            if self._evaluator is not None:
+                evaluator = self._evaluator
+            else:
+                model_path = self.init_model if self.init_model else os.path.join(MODEL_DIR, "current_policy.pkl")
+                try:
+                    self.policy_value_net = PolicyValueNet(model=model_path, **self.net_kwargs)
+                except Exception:
+                    self.policy_value_net = PolicyValueNet(**self.net_kwargs)
+                evaluator = self.policy_value_net.evaluator()
+            self.engine = SelfPlayEngine(evaluator, n_games=self.n_games, n_playout=self.n_playout,
+                                         c_puct=self.c_puct, temp=self.temp, seed=self.seed,
+                                         node_cap=self.node_cap, max_game_moves=self.max_game_moves)
+            self.packer = replay.ReplayPacker(self.engine.device, self.states_mode)
 
     def collect_data(self, is_shown=False):
-        """One lockstep move in every game slot; every game that finishes is packed (preprocess +
-        flip, collect.py:141-142) and appended.  Returns the running game count (collect.py:176)."""
+        """One lockstep move in every game slot; the games that finish with it are packed together
+        (preprocess + flip, collect.py:141-142: one upload, one K8 launch, one read-back per chunk) and
+        handed to the writer thread.  Returns the running game count (collect.py:176)."""
         self.load_model()
-        for rec in self.engine.play_move():
-            states, probs, winners = replay.pack_game(rec, self.states_mode, device=self.engine.device)
-            if self.h5 is not None:
-                index = distributed.global_game_index(self.local_games, self.rank, self.world)
-                self.h5.add(states, probs, winners, index=index if self.world > 1 else None)
-            if self.npy is not None:
-                self.npy.add(states, probs, winners)
-            self.episode_len = len(rec)
-            self.local_games += 1
+        finished = self.engine.play_move()
+        if finished:
+            for chunk in self.packer.pack(finished):
+                n = len(chunk.spans)
+                indices = None
+                if self.world > 1:
+                    indices = [distributed.global_game_index(self.local_games + i, self.rank, self.world) for i in range(n)]
+                if self.writer is not None:
+                    self.writer.submit(chunk, indices)
+                else:
+                    for k in range(n):
+                        states, probs, winners = chunk.game_arrays(k)
+                        if self.h5 is not None:
+                            self.h5.add(states, probs, winners, index=None if indices is None else indices[k])
+                        if self.npy is not None:
+                            self.npy.add(states, probs, winners)
+                    chunk.release()
+                self.local_games += n
+            self.episode_len = len(finished[-1])
             self.iters = self.local_games
         return self.iters
+
+    def flush(self):
+        """Everything collected so far is on disk and indexed (the trainer may open the files)."""
+        if self.writer is not None:
+            self.writer.drain()
+        else:
+            if self.h5 is not None:
+                self.h5.flush()
+            if self.npy is not None:
+                self.npy.flush()
 
     def run(self, is_shown=False, max_games=None):
         first = self.iters
@@ -92,8 +128,12 @@ class CollectPipeline:
         return self.iters
 
     def close(self):
+        if self.writer is not None:
+            self.writer.close()
+            self.writer = None
         if self.npy is not None:
-            self.npy.flush()
+            self.npy.close()
+            self.npy = None
         if self.h5 is not None:
             self.h5.close()
             self.h5 = None
@@ -108,7 +148,7 @@ def merge_h5_shards(shard_paths, out_path, gzip_level=4):
             for name in r.root_links():
                 games.append((int(name.split("_")[1]), p, name))
     games.sort()
-    out = h5lite.H5ReplayWriter(out_path, gzip_level=gzip_level, flush_every=64)
+    out = h5lite.H5ReplayWriter(out_path, gzip_level=gzip_level)
     for _, p, name in games:
         with h5lite.H5Reader(p) as r:
             d = r.read_group(name)

@@ -459,6 +459,8 @@ mcts_advance_compact_kernel(ccz_arena a, const int16_t *chosen) {
             const uint32_t hit = __ballot_sync(FULL, i < rnc && link_move(link_vec(a)[rfc + i].y) == mv);
             if (hit) child = rfc + base + __ffs(hit) - 1;
         }
+    } else if (mv == CCZ_ADVANCE_KEEP) {
+        child = a.d_root[g]; // idle slot: same position, same tree (compacted like any other)
     }
     if (child >= 0) {
         int p = -1;

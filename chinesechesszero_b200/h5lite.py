@@ -423,15 +423,34 @@ class H5Reader:
 
 
 class H5ReplayWriter:
-    """The reference's ``collect_data`` persistence (collect.py:146-169) on top of H5Writer."""
+    """The reference's ``collect_data`` persistence (collect.py:146-169) on top of H5Writer.
 
-    def __init__(self, path: str, gzip_level: int | None = 4, flush_every: int = 1):
+    The game data is appended as soon as ``add`` is called; the root group's INDEX (heap, symbol nodes,
+    B-tree, header: ~65 B per game, re-emitted whole because the v1 structures are written densely) and
+    the ``iters`` attribute are rewritten by ``flush``.  ``flush_every`` = N flushes after every N games
+    (1 = the reference's behaviour, one consistent file per game, at O(games^2) dead index bytes);
+    the default None flushes when ``max(64, games / 16)`` games are pending or ``flush_seconds`` have
+    passed, which keeps the dead index below ~1 KB per game, and always on ``close``.  A crash loses at
+    most the games since the last flush (their data is in the file but not linked)."""
+
+    def __init__(self, path: str, gzip_level: int | None = 4, flush_every: int | None = None,
+                 flush_seconds: float = 30.0):
+        import time
+
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         self.w = H5Writer(path, "a")
         self.gzip_level = gzip_level
         self.flush_every = flush_every
+        self.flush_seconds = float(flush_seconds)
         self.iters = int(self.w.attrs.get("iters", 0))
         self._pending = 0
+        self._clock = time.monotonic
+        self._last_flush = self._clock()
+        self.flushes = 0
+
+    @property
+    def n_groups(self) -> int:
+        return len(self.w.groups)
 
     def add(self, states, mcts_probs, winners, index: int | None = None) -> int:
         k = self.iters if index is None else int(index)
@@ -440,18 +459,26 @@ class H5ReplayWriter:
             {"states": np.asarray(states, dtype=np.float16), "mcts_probs": np.asarray(mcts_probs, dtype=np.float64),
              "winners": np.asarray(winners, dtype=np.float64)},
             gzip={"states": self.gzip_level, "mcts_probs": self.gzip_level, "winners": None})
-        self.iters = max(self.iters, k) + 1 if index is not None else self.iters + 1
+        self.iters = max(self.iters, k + 1) if index is not None else self.iters + 1
         self.w.attrs["iters"] = np.int64(self.iters)
         self._pending += 1
-        if self._pending >= self.flush_every:
-            self.w.flush()
-            self._pending = 0
+        if self.flush_every is not None:
+            due = self._pending >= self.flush_every
+        else:
+            due = (self._pending >= max(64, len(self.w.groups) // 16)
+                   or self._clock() - self._last_flush >= self.flush_seconds)
+        if due:
+            self.flush()
         return self.iters
 
     def flush(self):
-        self.w.flush()
+        if self._pending or self.w._dirty:
+            self.w.flush()
+            self.flushes += 1
         self._pending = 0
+        self._last_flush = self._clock()
         return self.iters
 
     def close(self):
+        self.flush()
         self.w.close()

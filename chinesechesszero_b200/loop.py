@@ -37,8 +37,9 @@ class SelfPlayTrainLoop:
         target = self.collect.iters + self.games_per_iteration
         while self.collect.iters < target:
             self.collect.collect_data()
-        samples = self.collect.npy.flush()
-        self.train.dataset = None                      # re-open the grown npy triple
+        self.train.dataset = None                      # drop the old memory maps, then re-open the grown npy triple
+        self.collect.flush()
+        samples = self.collect.npy.rows
         loss, entropy = self.train.policy_update()
         pv = self.collect.policy_value_net
         pv.policy_value_net.eval()

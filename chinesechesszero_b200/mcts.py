@@ -94,7 +94,6 @@ class MCTS:
         """mcts.py:131-166: n_playout playouts, then softmax(1/temp*log(visits+1e-10)) over the root
         children in generation order.  Returns (acts tuple, probs float64 array)."""
         self._sync_root(board)
-        self._search.ensure_capacity(self.n_playout, self._search.arena.pool_ctl.cpu().numpy())
         interval = max(1, self.n_playout // 100)  # progress throttle, mcts.py:148-160
         remaining = self.n_playout
         while remaining > 0:

@@ -151,28 +151,52 @@ class BatchedEvaluator:
         self.conv_events: list | None = None
         self.refresh(net)
 
+    def _keep(self, key: str, t: torch.Tensor) -> torch.Tensor:
+        """First call: adopt ``t``.  Later calls: copy into the tensor adopted under ``key`` so that its
+        device address never changes -- CUDA graphs captured by ``LockstepSearch.enable_graphs`` and the
+        search loops of other owners of this evaluator keep reading valid (and current) weights."""
+        old = self._params.get(key)
+        if old is not None and old.shape == t.shape and old.dtype == t.dtype and old.stride() == t.stride():
+            old.copy_(t)
+            return old
+        self._params[key] = t
+        return t
+
     @torch.no_grad()
     def refresh(self, net: Net) -> None:
-        """(Re)fold the weights of ``net`` (call after a training update)."""
+        """(Re)fold the weights of ``net`` (call after a training update).  In place: every folded tensor
+        keeps its storage, so captured graphs stay valid; ``version`` counts the refreshes."""
         dev, dt = self.device, self.dtype
         cl = torch.channels_last
+        if not hasattr(self, "_params"):
+            self._params: dict[str, torch.Tensor] = {}
+            self.version = 0
+        self.version += 1
+        keep = self._keep
 
-        def conv_params(conv, bn):
+        def conv_params(key, conv, bn):
             w, b = _fold(conv, bn)
-            return w.to(dev, dt).contiguous(memory_format=cl), b.to(dev, dt), b.to(dev, torch.float32).contiguous()
+            return (keep(key + ".w", w.to(dev, dt).contiguous(memory_format=cl)), keep(key + ".b", b.to(dev, dt)),
+                    keep(key + ".b32", b.to(dev, torch.float32).contiguous()))
 
-        self.stem = conv_params(net.conv_block, net.conv_block_bn)
+        self.stem = conv_params("stem", net.conv_block, net.conv_block_bn)
         # K10: with the tower on K9 the stem of search-time inputs is a table lookup over the board records
-        self.stem_lookup = stem_tables(self.stem[0], self.stem[2]) if self.conv_impl in ("k9", "k9_skip") else None
-        self.blocks = [(conv_params(rb.conv1, rb.conv1_bn), conv_params(rb.conv2, rb.conv2_bn))
-                       for rb in net.res_blocks]
+        if self.conv_impl in ("k9", "k9_skip"):
+            table, bias_turn = stem_tables(self.stem[0], self.stem[2])
+            self.stem_lookup = (keep("stem.table", table), keep("stem.bias_turn", bias_turn))
+        else:
+            self.stem_lookup = None
+        self.blocks = [(conv_params(f"rb{i}.1", rb.conv1, rb.conv1_bn), conv_params(f"rb{i}.2", rb.conv2, rb.conv2_bn))
+                       for i, rb in enumerate(net.res_blocks)]
         # both 1x1 heads in one convolution: 17 policy + 7 value channels
         pw, pb = _fold(net.policy_conv, net.policy_bn)
         vw, vb = _fold(net.value_conv, net.value_bn)
-        self.heads_w = torch.cat([pw, vw], 0).to(dev, dt).contiguous(memory_format=cl)
-        self.heads_b = torch.cat([pb, vb], 0).to(dev, dt)
-        self.policy_fc = (net.policy_fc.weight.detach().to(dev, dt), net.policy_fc.bias.detach().to(dev, torch.float32))
-        self.value_fc1 = (net.value_fc1.weight.detach().to(dev, dt), net.value_fc1.bias.detach().to(dev, dt))
+        self.heads_w = keep("heads.w", torch.cat([pw, vw], 0).to(dev, dt).contiguous(memory_format=cl))
+        self.heads_b = keep("heads.b", torch.cat([pb, vb], 0).to(dev, dt))
+        self.policy_fc = (keep("pfc.w", net.policy_fc.weight.detach().to(dev, dt).clone()),
+                          keep("pfc.b", net.policy_fc.bias.detach().to(dev, torch.float32).clone()))
+        self.value_fc1 = (keep("vfc1.w", net.value_fc1.weight.detach().to(dev, dt).clone()),
+                          keep("vfc1.b", net.value_fc1.bias.detach().to(dev, dt).clone()))
         # 16-byte-aligned GEMM operands for the two FC layers: K = 17*90 = 1530 and 7*90 = 630 give row strides that
         # are not multiples of 16 bytes, which sends cuBLAS to a legacy sm80 kernel (113 us for the policy FC at 4096
         # leaves).  Zero-padded copies: K -> 1536 / 640, policy N -> 2088.
@@ -181,16 +205,17 @@ class BatchedEvaluator:
         wp[:N_ACTIONS, :PLAYS * 90] = self.policy_fc[0]
         wv = torch.zeros((self.value_fc1[0].shape[0], self._kv), dtype=dt, device=dev)
         wv[:, :PIECES * 90] = self.value_fc1[0]
-        self._fc_pad = (wp, wv)
-        self._head_buf = {}
+        self._fc_pad = (keep("pfc.pad", wp), keep("vfc1.pad", wv))
+        if not hasattr(self, "_head_buf"):
+            self._head_buf = {}
         # the fused 1x1 heads as one GEMM over the NHWC pixel rows: [g*90, C] x [C, 24 -> 32] (+ bias)
         hw = torch.zeros((32, self.heads_w.shape[1]), dtype=dt, device=dev)
         hw[:PLAYS + PIECES] = self.heads_w.reshape(PLAYS + PIECES, -1)
         hb = torch.zeros((32,), dtype=dt, device=dev)
         hb[:PLAYS + PIECES] = self.heads_b
-        self._heads_gemm = (hw, hb)
-        self.value_fc2 = (net.value_fc2.weight.detach().to(dev, torch.float32),
-                          net.value_fc2.bias.detach().to(dev, torch.float32))
+        self._heads_gemm = (keep("heads.gemm_w", hw), keep("heads.gemm_b", hb))
+        self.value_fc2 = (keep("vfc2.w", net.value_fc2.weight.detach().to(dev, torch.float32).clone()),
+                          keep("vfc2.b", net.value_fc2.bias.detach().to(dev, torch.float32).clone()))
 
     def _k9(self, x, w, b32, skip, out):
         if self.conv_events is None:

@@ -120,13 +120,14 @@ class LockstepSearch:
             self._graphs = {}
         return True
 
-    def ensure_capacity(self, n_playout: int, ctl: np.ndarray | None = None) -> None:
+    def ensure_capacity(self, n_playout: int, ctl: np.ndarray | None = None, ctl_lag: int = 0) -> None:
         """Make room for a search of ``n_playout`` playouts in every game.  Geometry first (the pool must
         hold the worst case of a fresh tree per game); then, if ``ctl`` (a host copy of ``arena.pool_ctl``
-        taken after the last advance) shows fewer free pages than the worst case, the pool doubles.  Callers
-        that never synchronise skip this and rely on the guard in ``run``."""
+        taken after the last advance) shows fewer free pages than the worst case, the pool doubles; a
+        snapshot that is ``ctl_lag`` searches old is charged the worst case of those searches as well."""
         w = self.search_pages(n_playout)
         floor = self.n_games * (w + 1)
+        pages_at_snapshot = self.arena.n_pages
         if self.arena.n_pages < floor or self.arena.max_pages < w + 1:
             ok = floor <= self.max_pool_pages and self._grow(min(max(floor, 2 * self.arena.n_pages), self.max_pool_pages))
             if not ok or self.arena.max_pages < w + 1:
@@ -135,10 +136,12 @@ class LockstepSearch:
                     f"{1 << self.page_shift} nodes ({w + 1} per game), the pool has {self.arena.n_pages} "
                     f"(raise nodes_per_game / max_pool_nodes)")
         if ctl is not None:
-            free = int(ctl[_lib.CTL_TAIL] - ctl[_lib.CTL_HEAD])
-            if free < self.n_games * w:
+            # pages added by the geometric growth above are all free
+            free = int(ctl[_lib.CTL_TAIL] - ctl[_lib.CTL_HEAD]) + self.arena.n_pages - pages_at_snapshot
+            need = self.n_games * w * (1 + int(ctl_lag))
+            if free < need:
                 used = self.arena.n_pages - free
-                self._grow(max(2 * self.arena.n_pages, used + self.n_games * w))
+                self._grow(max(2 * self.arena.n_pages, used + need))
 
     def pool_stats(self) -> dict:
         st = self.arena.pool_stats()
@@ -165,10 +168,18 @@ class LockstepSearch:
         policy, kind, values = evaluator(self.planes if need else None, self.leaf_boards)
         self.expand_backup(policy, kind, values)
 
-    def run(self, evaluator, n_playout: int) -> None:
+    def run(self, evaluator, n_playout: int, ctl: np.ndarray | None = None, may_sync: bool = True,
+            ctl_lag: int = 0) -> None:
+        """``n_playout`` playouts in every game.  Capacity first: ``ctl`` is a host copy of
+        ``arena.pool_ctl`` taken after the last advance (SelfPlayEngine reads it back with the move's other
+        results); without it the counters are read here (one 64-byte device-to-host copy) unless
+        ``may_sync=False`` (the device-resident path: no host synchronisation; it passes the newest snapshot
+        that has already arrived, ``ctl_lag`` searches old, and the pool grows that much earlier)."""
         if n_playout <= 0:
             return
-        self.ensure_capacity(n_playout)  # geometry only: no synchronisation
+        if ctl is None and may_sync:
+            ctl = self.arena.pool_ctl.cpu().numpy()
+        self.ensure_capacity(n_playout, ctl, ctl_lag)
         # device-side guard: after it no expansion of this search can fail (see ccz_mcts_reserve)
         _lib.mcts_reserve(self.arena, self.search_pages(n_playout))
         if self._graphs is not None and self._graph_evaluator is evaluator and n_playout > 0:

@@ -69,9 +69,10 @@ class SelfPlayEngine:
             # n_playout expansions of ~41 (at most 119) children on top of the sub-tree kept by the last advance().
             # Measured with a near-uniform policy at 400 playouts: median live tree 23k nodes, p99 35k, and a
             # tail of forced-reply sequences beyond 65k -- which a pool absorbs because only the
-            # SUM over the games has to fit.  6x the mean growth per move leaves the worst-case reservation of
-            # every game (119 children per playout) on top of a 2x mean live tree; the pool doubles on demand.
-            nodes_per_game = max(4096, int(self.n_playout * 41 * 6))
+            # SUM over the games has to fit (soak test: 60 moves, median peak 50k, p99 95k, max 127k).  8x the
+            # mean growth per move = the worst-case reservation of every game (119 children per playout, ~51k
+            # nodes at 400 playouts) on top of an 80k mean live tree; the pool doubles on demand.
+            nodes_per_game = max(4096, int(self.n_playout * 41 * 8))
         self.search = LockstepSearch(n_games, nodes_per_game=nodes_per_game, device=device, c_puct=c_puct,
                                      page_shift=page_shift, max_pool_nodes=max_pool_nodes)
         if use_graphs:  # replay the lockstep step from CUDA graphs (capture-safe evaluators only)
@@ -119,8 +120,7 @@ class SelfPlayEngine:
         s = self.search
         # the pool counters read back with the last move tell whether this search fits: grow the pool (trees
         # migrate, nothing is lost) instead of letting the device-side guard drop sub-trees
-        s.ensure_capacity(self.n_playout, self._h_ctl.numpy() if self._ctl_valid else None)
-        s.run(self.evaluator, self.n_playout)
+        s.run(self.evaluator, self.n_playout, ctl=self._h_ctl.numpy() if self._ctl_valid else None)
         acts_d, visits_d, counts_d = s.root_visits()
         self._h_acts.copy_(acts_d, non_blocking=True)
         self._h_visits.copy_(visits_d, non_blocking=True)
@@ -234,7 +234,7 @@ class SelfPlayEngine:
                 chosen=torch.zeros(g, dtype=torch.int16, device=dev),
                 # device ring of per-move samples (what play_move() hands to the host every move):
                 # positions searched, root actions, un-noised pi, counts, moves played, finished mask
-                ring=self.resident_ring, head=0, filled=0,
+                ring=self.resident_ring, head=0, filled=0, ctl_snaps=[],
                 ring_boards=torch.zeros((self.resident_ring, g, _lib.BOARD_BYTES), dtype=torch.uint8, device=dev),
                 ring_acts=torch.zeros((self.resident_ring, g, _lib.MAX_MOVES), dtype=torch.int16, device=dev),
                 ring_pi=torch.zeros((self.resident_ring, g, _lib.MAX_MOVES), dtype=torch.float64, device=dev),
@@ -252,7 +252,14 @@ class SelfPlayEngine:
         path bench.py times for ``value``; ``play_move`` is the host-facing one timed for ``e2e``."""
         s, r = self.search, self._resident_state()
         g = self.n_games
-        s.run(self.evaluator, self.n_playout)
+        # pool counters: the snapshot enqueued one move ago has arrived by now (the host runs at most a launch
+        # queue ahead of the device), the one of the last move usually has not -- no waiting either way
+        ctl, lag = None, 0
+        for age, (ev_done, buf) in enumerate(reversed(r["ctl_snaps"])):
+            if ev_done.query():
+                ctl, lag = buf.numpy(), age
+                break
+        s.run(self.evaluator, self.n_playout, ctl=ctl, may_sync=False, ctl_lag=lag)
         acts, visits, counts = s.root_visits()
         valid = r["idx"] < counts.view(g, 1)
         lo_temp = max(0.1, self.temp * 0.5)
@@ -287,6 +294,11 @@ class SelfPlayEngine:
         if r["filled"] == r["ring"]:  # never overwrite samples: a full ring goes to the host backlog
             self.resident_backlog.append(self.drain_resident())
         s.reset(self._d_mask)
+        ev_done, buf = r["ctl_snaps"].pop(0) if len(r["ctl_snaps"]) >= 3 else (torch.cuda.Event(), torch.zeros(
+            (_lib.CTL_WORDS,), dtype=torch.int64, pin_memory=True))
+        buf.copy_(s.arena.pool_ctl, non_blocking=True)
+        ev_done.record()
+        r["ctl_snaps"].append((ev_done, buf))
         r["move_count"] = torch.where(over, torch.zeros_like(mc), mc)
         r["finished"] += over.sum()
         self.total_moves += g

@@ -166,7 +166,7 @@ class TrainPipeline:
         torch.nn.utils.clip_grad_norm_(net.parameters(), 5.0)
         opt.step()
         out = {"loss": float(loss.detach()), "policy_loss": float(policy_loss.detach()), "value_loss": float(value_loss.detach()),
-               "rolled_back": False, "kl": None, "entropy": None}
+               "rolled_back": False, "counted": False, "kl": None, "entropy": None}
         if (torch.isnan(loss) or torch.isinf(loss) or torch.isnan(log_act_probs).any()
                 or torch.isinf(log_act_probs).any()):
             self._backup.restore(net, opt)
@@ -180,6 +180,7 @@ class TrainPipeline:
         with torch.no_grad():
             lp = log_act_probs.float()
             out["entropy"] = float(-torch.mean(torch.sum(torch.exp(lp) * lp, dim=1)))
+        out["counted"] = True  # train.py:247-254: the epoch totals take the batch BEFORE the entropy guard looks at it
         if out["entropy"] < self.min_entropy_guard:
             if float((mcts_probs_batch > 0).sum(dim=1).float().mean()) > 1.5:
                 self._backup.restore(net, opt)
@@ -199,7 +200,7 @@ class TrainPipeline:
         n = 0
         for batch in self.dataset.batches(self.batch_size, shuffle=True, generator=generator):
             r = self.train_step(*batch)
-            if r["rolled_back"]:
+            if not r["counted"]:  # NaN / inf roll-back (train.py:211-221); entropy-guard roll-backs are counted
                 continue
             tot["loss"] += r["loss"]
             tot["entropy"] += r["entropy"]

@@ -60,6 +60,7 @@ typedef struct CUstream_st *ccz_stream_t; /* == cudaStream_t */
 /* special values of d_chosen[g] in ccz_mcts_advance */
 #define CCZ_ADVANCE_NEW_GAME (-1)  /* start position, fresh root */
 #define CCZ_ADVANCE_DROP_TREE (-2) /* keep the position, fresh root */
+#define CCZ_ADVANCE_KEEP (-3)      /* keep the position and the tree (a slot that does not move) */
 
 /* A tree node is two records so that one 16-byte load per lane brings everything PUCT needs of a
  * child (N, Q, P) plus the link to ITS children, and the cold fields stay out of that stream. */
@@ -187,7 +188,8 @@ int ccz_mcts_root_visits(const ccz_arena *a, int16_t *d_acts /*[n,128]*/,
  * is compacted breadth-first into fresh pages (tree reuse; visit counts and Q carry over), the
  * pages of the rest go back to the pool, the root board and key window advance.
  * CCZ_ADVANCE_NEW_GAME resets game g to the start position with a fresh root,
- * CCZ_ADVANCE_DROP_TREE keeps the position but drops the tree; an id that is not a root child
+ * CCZ_ADVANCE_DROP_TREE keeps the position but drops the tree, CCZ_ADVANCE_KEEP leaves the slot
+ * as it is; an id that is not a root child
  * gives a fresh root as in the reference (mcts.py:177-178). */
 int ccz_mcts_advance(const ccz_arena *a, const int16_t *d_chosen, ccz_stream_t s);
 

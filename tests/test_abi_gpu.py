@@ -115,7 +115,7 @@ def test_resident_move_path_matches_host_path_in_deterministic_mode():
 
 def test_cuda_graph_replay_equals_eager_search():
     """The captured lockstep step (K3 -> K1 -> bf16 forward -> K4/K5) replayed from CUDA graphs gives
-    the same trees as eager launches, across an advance (second arena side, second graph)."""
+    the same trees as eager launches, across advances (the graph holds the pool's pointers, not the trees)."""
     from chinesechesszero_b200.net import BatchedEvaluator, Net
     from chinesechesszero_b200.search import LockstepSearch
 
@@ -131,9 +131,41 @@ def test_cuda_graph_replay_equals_eager_search():
             s.run(ev, 25)
             s.check_status()
             acts, visits, counts = s.root_visits()
-            res.append((acts.clone(), visits.clone(), s.arena.value[: 16 * 8192: 8192].clone()))
+            res.append((acts.clone(), visits.clone(), s.arena.nodes[s.arena.root.long(), 1].clone()))  # root Q bits
             chosen = acts.gather(1, visits.argmax(1, keepdim=True).long()).view(-1).contiguous()
             s.advance(chosen)
         outs.append(res)
     for (a0, v0, q0), (a1, v1, q1) in zip(*outs):
         assert torch.equal(a0, a1) and torch.equal(v0, v1) and torch.equal(q0, q1)
+
+
+def test_graph_replay_follows_refreshed_weights():
+    """after a training update BatchedEvaluator.refresh() re-folds the weights IN PLACE, so the
+    CUDA graph captured before the update replays with the new weights (equal to an eager search over a
+    fresh evaluator of the updated net), not with freed storage."""
+    from chinesechesszero_b200.net import BatchedEvaluator, Net
+    from chinesechesszero_b200.search import LockstepSearch
+    from oracle import net_oracle
+
+    torch.manual_seed(2)
+    net = Net(num_channels=32, resblocks_num=2).cuda().eval()
+    ev = BatchedEvaluator(net)
+    s = LockstepSearch(n_games=8, nodes_per_game=8192)
+    s.enable_graphs(ev)
+    s.run(ev, 12)                      # captures the graph
+    assert s._graphs.get(0) is not None
+    old_visits = s.root_visits()[1].clone()
+    net_oracle.perturb_(net.state_dict(), seed=5)   # "one training step"
+    torch.cuda.empty_cache()
+    ev.refresh(net)
+    junk = [torch.randn(1 << 20, device="cuda") for _ in range(8)]  # would land in freed weight blocks
+    s.reset()
+    s.run(ev, 12)                      # graph replay with refreshed weights
+    got = [t.clone() for t in s.root_visits()[:2]]
+    ref = LockstepSearch(n_games=8, nodes_per_game=8192)
+    ev2 = BatchedEvaluator(net)
+    ref.run(ev2, 12)                   # eager, fresh evaluator
+    want = ref.root_visits()[:2]
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    assert not torch.equal(got[1], old_visits)
+    del junk

@@ -62,6 +62,33 @@ def test_bn_folding_is_exact_in_fp32_on_cpu():
     assert torch.allclose(v, v_o.view(-1), atol=1e-5)
 
 
+def test_refresh_is_in_place_on_cpu():
+    """refresh() must not rebind the folded tensors (captured CUDA graphs and other owners of
+    the evaluator hold their addresses); the outputs must follow the new weights."""
+    from chinesechesszero_b200.net import BatchedEvaluator, Net
+
+    torch.manual_seed(4)
+    net = Net(num_channels=32, resblocks_num=2).eval()
+    ev = BatchedEvaluator(net, device="cpu", dtype=torch.float32, fused_epilogue=False)
+    ptrs = {k: t.data_ptr() for k, t in ev._params.items()}
+    blocks_before = [[t.data_ptr() for t in c] for pair in ev.blocks for c in pair]
+    x = torch.rand(3, 17, 7, 10, 9)
+    before = ev.forward(x)
+    net_oracle.perturb_(net.state_dict(), seed=11)
+    ev.refresh(net)
+    assert ev.version == 2
+    assert {k: t.data_ptr() for k, t in ev._params.items()} == ptrs
+    assert [[t.data_ptr() for t in c] for pair in ev.blocks for c in pair] == blocks_before
+    logits, v = ev.forward(x)
+    logp_o, v_o = net_oracle.forward(net.state_dict(), x)
+    assert torch.allclose(torch.log_softmax(logits, 1), logp_o, atol=1e-4) and torch.allclose(v, v_o.view(-1), atol=1e-5)
+    assert not torch.allclose(logits, before[0])
+    # the evaluator does not alias the module's parameters: training the net does not leak in before refresh()
+    with torch.no_grad():
+        net.value_fc2.weight.add_(1.0)
+    assert torch.equal(ev.forward(x)[1], v)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["seed0", "perturbed"])
 @pytest.mark.parametrize("conv_impl", ["k9", "k9_skip", "cudnn", "torch"])

@@ -42,15 +42,17 @@ def board_hash_evaluator(n_games, seed=0, scale=1.0):
     return evaluator
 
 
+@pytest.mark.parametrize("nodes_per_game", [1 << 17, 2048])
 @pytest.mark.parametrize("name", scenario_names())
-def test_tiny_pages_equal_reference_golden(name, golden_dir):
+def test_tiny_pages_equal_reference_golden(name, nodes_per_game, golden_dir):
     """page_shift=7: a page holds one or two child runs, so almost every expansion pops a page and every
-    advance compacts across many pages -- results must not change."""
+    advance compacts across many pages -- results must not change.  With 2048 nodes per game the pool is
+    far too small and grows (ccz_mcts_migrate) before the first and between later searches."""
     from chinesechesszero_b200.search import LockstepSearch
 
     sc = next(s for s in load_golden(golden_dir)["scenarios"] if s["name"] == name)
     G = 2
-    search = LockstepSearch(n_games=G, nodes_per_game=8192, page_shift=7, c_puct=float(sc["c_puct"]))
+    search = LockstepSearch(n_games=G, nodes_per_game=nodes_per_game, page_shift=7, c_puct=float(sc["c_puct"]))
     rec = np.array(sc["root_record"], dtype=np.uint8)
     search.set_roots(np.tile(rec, (G, 1)))
     id_of = cs.action_table()[0]
@@ -72,6 +74,7 @@ def test_tiny_pages_equal_reference_golden(name, golden_dir):
         pool_accounting(search.arena)
     st = search.pool_stats()
     assert st["expand_failed"] == 0 and st["trees_dropped"] == 0
+    assert (st["pool_grown"] >= 1) == (nodes_per_game == 2048)
 
 
 def test_migrate_keeps_trees_and_search_continues_bit_identically():
@@ -118,21 +121,20 @@ def test_reserve_guard_drops_only_the_largest_trees():
                        max_pool_nodes=pool_pages << shift)
     assert s.arena.n_pages == pool_pages
     ev = board_hash_evaluator(G, seed=5)
-    # games 0..3: a root with ONE legal reply (advancing keeps the whole tree); games 4..7: start position
-    forced = positions.record_from_fen("3k5/9/9/9/9/9/9/9/9/3R1K3 b")
-    s.set_roots(np.stack([forced] * 4 + [cs.start_record()] * 4))
     s.run(ev, P)
     assert s.pool_stats()["trees_dropped"] == 0
-    # keep everything in games 0..3 (advance along the only child), restart games 4..7
-    acts, visits, _ = s.root_visits()
-    chosen = acts.gather(1, visits.argmax(1, keepdim=True).long()).view(-1).clone()
-    chosen[4:] = -1
-    s.advance(chosen.contiguous())
+    # games 0..3 keep their whole tree (CCZ_ADVANCE_KEEP: ~20 pages each), games 4..7 restart (1 page each)
+    keep_before = [walk_tree(s.arena, g) for g in range(4)]
+    s.advance(np.array([_lib.ADVANCE_KEEP] * 4 + [_lib.ADVANCE_NEW_GAME] * 4, dtype=np.int16))
+    for g in range(4):
+        after = walk_tree(s.arena, g)
+        for key in ("visits", "value", "prior", "move", "n_child", "depth"):
+            assert np.array_equal(keep_before[g][key], after[key]), (g, key)
     boards_before = s.root_boards.cpu().numpy().copy()
     pages_before = [len(game_pages(s.arena, g)) for g in range(G)]
     free_before = s.pool_stats()["free_pages"]
     assert free_before < G * w                 # short: the guard has to act
-    s.run(ev, P)                               # guard + search
+    s.run(ev, P, may_sync=False)               # device-side guard alone (the resident path) + search
     st = s.pool_stats()
     status = s.arena.status.cpu().numpy()
     share = pool_pages // G - w
@@ -171,7 +173,6 @@ def test_forced_reply_roots_keep_their_subtrees():
     kept = np.zeros(G, dtype=np.int64)
     peak = 0
     for move in range(12):
-        s.ensure_capacity(P, s.arena.pool_ctl.cpu().numpy())
         s.run(ev, P)
         s.check_status()
         acts, visits, counts = (t.cpu().numpy() for t in s.root_visits())
@@ -210,8 +211,7 @@ def test_soak_4096_games_400_playouts_60_moves():
     games = 0
     for move in range(MOVES):
         # replicate play_move() but look at the visit sums before the move is chosen
-        s.ensure_capacity(P, eng._h_ctl.numpy() if eng._ctl_valid else None)
-        s.run(eng.evaluator, P)
+        s.run(eng.evaluator, P, ctl=eng._h_ctl.numpy() if eng._ctl_valid else None)
         _, visits_d, _ = s.root_visits()
         vs = visits_d.sum(1).cpu().numpy()
         expect = np.where(kept > 0, kept - 1 + P, P - 1)
