@@ -56,7 +56,13 @@ def parse_args():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU (configs[2]: 4096)")
     ap.add_argument("--playouts", type=int, default=400)
-    ap.add_argument("--node-cap", type=int, default=65536)
+    ap.add_argument("--nodes-per-game", type=int, default=None,
+                    help="average node budget per game of the shared MCTS page pool (default: 8 x 41 x playouts)")
+    ap.add_argument("--max-game-moves", type=int, default=24,
+                    help="self-play games are cut after this many moves and the slots start staggered, so that games "
+                         "finish (and their replay is packed and written) at the steady-state rate inside the timed regions")
+    ap.add_argument("--replay-dir", default=None, help="where the e2e arm writes data.h5 (default: a temporary directory)")
+    ap.add_argument("--no-replay", action="store_true", help="e2e without replay packing / writing")
     ap.add_argument("--movegen-positions", type=int, default=1 << 20)
     ap.add_argument("--no-movegen", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -130,46 +136,58 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(n_moves: int, n_playout: int):
-    """The reference's collect.py path on the host cores (oracle port; kind "port")."""
+def _reference_player(n_playout: int, cores: int):
+    """(player, kind, what): the unmodified reference (oracle/_ref snapshot or /root/reference) when present,
+    else the oracle port of the collect path."""
+    from oracle import reference_arm
+
+    if reference_arm.available():
+        return (reference_arm.ReferenceSelfPlay(n_playout=n_playout, threads=cores), "reference",
+                "UNMODIFIED reference modules (net.PolicyValueNet(use_gpu=False) CPU branch, mcts.MCTS_AI, the loop body of "
+                "Game.start_self_play) with cchess replaced by the C-backed shim (favours the reference)")
     from oracle import collect_oracle
 
+    return (collect_oracle.PortedSelfPlay(n_playout=n_playout, threads=cores), "port",
+            "CPU port of collect.py -> game.py -> mcts.py -> net.py (shim board, flat search, fp32 batch-1 forward per playout)")
+
+
+def cpu_baseline(n_moves: int, n_playout: int):
+    """The reference's collect.py path on the host cores, bounded sample (the first moves of one game)."""
     cores = os.cpu_count() or 1
-    mps, secs, evals = collect_oracle.time_moves(n_moves, n_playout=n_playout, threads=cores)
-    return {"value": mps, "unit": UNIT, "cores": cores, "kind": "port",
+    sp, kind, what = _reference_player(n_playout, cores)
+    sp.policy_value_net.policy_value_fn(sp.game.board) if kind == "reference" else sp.policy_value_fn(sp.board)  # page in
+    t0 = time.perf_counter()
+    for _ in range(n_moves):
+        sp.play_move()
+    secs = time.perf_counter() - t0
+    return {"value": n_moves / secs, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"first {n_moves} move(s) of one self-play game from the start position, {n_playout} playouts "
-                      f"each, batch-1 fp32 forward per playout ({evals} evals, {secs:.1f} s); cchess replaced by the "
-                      "C-backed shim (favours the reference)"}
+                      f"each, batch-1 fp32 forward per playout, {secs:.1f} s; {what}"}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import collect_oracle
-
     cores = os.cpu_count() or 1
-    sp = collect_oracle.PortedSelfPlay(n_playout=args.playouts, threads=cores)
-    warm = min(args.warmup, 1)  # one full CPU move is ~15 s: a single warm-up move pages everything in
-    for _ in range(warm):
+    sp, kind, what = _reference_player(args.playouts, cores)
+    for _ in range(args.warmup):
         sp.play_move()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         sp.play_move()
     dt = time.perf_counter() - t0
     v = args.steps / dt
-    sample = (f"{args.steps} consecutive move(s) of one self-play game, {args.playouts} playouts each, tree reuse, "
-              f"batch-1 fp32 forward per playout on {cores} host threads")
+    sample = (f"{args.steps} consecutive move(s) of one self-play game after {args.warmup} warm-up move(s), {args.playouts} playouts "
+              f"each, tree reuse, batch-1 fp32 forward per playout on {cores} host threads; {what}")
     print(json.dumps({
         "impl": "reference", "metric": metric_name(args.playouts), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": warm, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init net, torch.manual_seed(0))",
         "config": {"workload": workload_name(args.games, args.playouts), "games_per_gpu": args.games, "n_playout": args.playouts,
                    "sample": "the reference plays its games one after the other (collect.py:138): each step is one move of ONE of the "
-                             f"{args.games} games, {args.playouts} playouts, through the CPU port of collect.py -> game.py -> mcts.py -> "
-                             "net.py (shim board, flat search, fp32 batch-1 forward per playout); moves/s of one game = the reference's "
-                             "whole-job rate on this host"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                             f"{args.games} games, {args.playouts} playouts; moves/s of one game = the reference's whole-job rate on this host"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -279,6 +297,7 @@ def bench_train(torch, batch: int = 512, steps: int = 5):
 
 
 def run_own_arm(args):
+    import numpy as np
     import torch
 
     from chinesechesszero_b200 import distributed as D
@@ -333,8 +352,8 @@ def run_own_arm(args):
             return out
 
     ev = base_eval if args.graphs else TimedEvaluator()
-    eng = SelfPlayEngine(ev, n_games=G, n_playout=P, node_cap=args.node_cap, seed=D.rank_seed(1234, rank),
-                         use_graphs=args.graphs)
+    M = max(2, args.max_game_moves)
+    stagger = np.arange(G, dtype=np.int64) % M   # slot g behaves as if its current game were `stagger[g]` moves old
 
     def barrier():
         D.barrier()
@@ -343,54 +362,112 @@ def run_own_arm(args):
     def max_over_ranks(ms: float) -> float:
         return D.max_over_ranks(ms, device="cuda")
 
-    # ---- warm-up: W full moves (device-resident path) + one host-path move -------------------
-    for _ in range(args.warmup):
-        eng.play_move_resident()
-    eng.play_move()
-    barrier()
+    # =========== arm A: `e2e` -- the user-facing pipeline (CollectPipeline.collect_data) ===========
+    # per move: search, visit counts / boards / flags read back to pinned host memory, host-side visit softmax + seeded
+    # Dirichlet choice, chosen moves uploaded, re-root, terminal test, slot refill; every game that finishes is packed
+    # by K8 (one upload, one launch, one read-back per chunk) and written to data.h5 (reference layout, gzip) by the
+    # writer thread.  The timed region ends when the file is flushed.
+    import shutil
+    import tempfile
 
-    # ---- timed region 1: `value`, everything resident in HBM --------------------------------
+    from chinesechesszero_b200.collect import CollectPipeline
+
+    tmp_dir = None
+    replay_dir = args.replay_dir
+    if replay_dir is None and not args.no_replay:
+        replay_dir = tmp_dir = tempfile.mkdtemp(prefix=f"ccz_bench_rank{rank}_")
+    pipe = CollectPipeline(n_games=G, n_playout=P, data_dir=replay_dir or tempfile.gettempdir(), states_mode="per_move",
+                           seed=D.rank_seed(1234, rank), node_cap=args.nodes_per_game, max_game_moves=M, rank=rank, world=world,
+                           write_h5=not args.no_replay, write_npy=False, evaluator=ev)
+    pipe.load_model()
+    eng = pipe.engine
+    if args.graphs:
+        eng.search.enable_graphs(ev)
+    eng.move_count[:] = stagger
+    e2e_warmup = min(args.warmup, 2)  # first-call costs only (the staggered slots are in steady state from move 1);
+    for _ in range(e2e_warmup):       # the W warm-up moves of the contract precede the `value` region below
+        pipe.collect_data()
+    pipe.flush()
+    barrier()
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
-    if not args.graphs:
-        ev.on = True
+    h2d0, d2h0 = eng.h2d_bytes + pipe.packer.h2d_bytes, eng.d2h_bytes + pipe.packer.d2h_bytes
+    games0 = pipe.iters
+    w = pipe.writer
+    wr0 = (w.games, w.samples, w.raw_bytes, w.busy_seconds) if w is not None else (0, 0, 0, 0.0)
+    file0 = os.path.getsize(pipe.data_path) if (pipe.h5 is not None and os.path.exists(pipe.data_path)) else 0
+    pack_launch0 = pipe.packer.launches
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     s0.record()
     for _ in range(args.steps):
-        eng.play_move_resident()
+        pipe.collect_data()
+    pipe.flush()            # replay of every finished game compressed, written and indexed
     s1.record()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_dev_ms = s0.elapsed_time(s1)
+    e2e_value = world * G * args.steps / e2e_ms * 1e3
+    h2d = (eng.h2d_bytes + pipe.packer.h2d_bytes - h2d0) / args.steps
+    d2h = (eng.d2h_bytes + pipe.packer.d2h_bytes - d2h0) / args.steps
+    pack_launches = pipe.packer.launches - pack_launch0
+    replay_info = None
+    if w is not None:
+        file1 = os.path.getsize(pipe.data_path)
+        replay_info = {
+            "games_written": w.games - wr0[0], "samples_written": w.samples - wr0[1],
+            "raw_mb_per_s": (w.raw_bytes - wr0[2]) / 1e6 / (e2e_ms / 1e3), "file_mb": (file1 - file0) / 1e6,
+            "writer_busy_frac": (w.busy_seconds - wr0[3]) / (e2e_ms / 1e3),
+            "format": "reference data.h5 layout (game_{k}/states f16 gzip, mcts_probs f64 gzip, winners f64, attr iters), per-rank shard",
+            "k8_launches": pack_launches,
+        }
+    pool_e2e = eng.pool_events()
+    games_finished = pipe.iters - games0
+    pipe.close()
+    if tmp_dir is not None:
+        shutil.rmtree(tmp_dir, ignore_errors=True)
+    del pipe, eng
+    torch.cuda.empty_cache()
+
+    # =========== arm B: `value` -- the same lockstep move with every input and output resident in HBM ===========
+    # visit softmax, Dirichlet mix, sampling, re-root, terminal test and refill on the device, no host synchronisation;
+    # the per-move samples go to a device ring that is drained to the host INSIDE the timed region.
+    eng = SelfPlayEngine(ev, n_games=G, n_playout=P, nodes_per_game=args.nodes_per_game, seed=D.rank_seed(4321, rank),
+                         use_graphs=args.graphs, max_game_moves=M, resident_ring=max(4, min(args.steps, 32)))
+    eng._resident_state()["move_count"].copy_(torch.from_numpy(stagger))
+    for _ in range(args.warmup):
+        eng.play_move_resident()
+    eng.resident_backlog.clear()
+    eng.drain_resident()
+    barrier()
+    if not args.graphs:
+        ev.on = True
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0.record()
+    for _ in range(args.steps):
+        eng.play_move_resident()
+    eng.resident_backlog.append(eng.drain_resident())
+    v1.record()
     barrier()
     if not args.graphs:
         ev.on = False
-    dev_ms = max_over_ranks(s0.elapsed_time(s1))
     clocks = sampler.stop() if sampler else None
+    s0_s1_ms = v0.elapsed_time(v1)
+    dev_ms = max_over_ranks(s0_s1_ms)
+    value = world * G * args.steps / dev_ms * 1e3
+    resident_samples = sum(int(d["boards"].shape[0]) for d in eng.resident_backlog) * G
+    pool_value = eng.pool_events()
     if args.graphs:
         # events cannot sit inside a captured graph: attribute the whole step to the forward, which
-        # gives a lower bound on its throughput (its live share is 0.994 in the eager run)
-        fwd_ms = [s0.elapsed_time(s1) / (args.steps * P)]
+        # gives a lower bound on its throughput (its live share is 0.99 in the eager run)
+        fwd_ms = [s0_s1_ms / (args.steps * P)]
+        conv_ms = []
     else:
         fwd_ms = [a.elapsed_time(b) for a, b in ev.pairs]
         conv_ms = [(sk, a.elapsed_time(b)) for sk, a, b in ev.conv]
         ev.pairs, ev.conv = [], []
     fwd_avg = sum(fwd_ms) / len(fwd_ms)
     n_fwd = len(fwd_ms)
-    eng.search.check_status()
-    value = world * G * args.steps / dev_ms * 1e3
-    drained = eng.drain_resident()  # untimed: the per-move samples the resident path kept on the device
-    resident_samples = int(drained["boards"].shape[0]) * G
-
-    # ---- timed region 2: `e2e`, host-facing API (D2H visit read-back, host move choice, H2D) ----
-    h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.play_move()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    eng.search.check_status()
-    e2e_value = world * G * args.steps / e2e_ms * 1e3
-    h2d = (eng.h2d_bytes - h2d0) / args.steps
-    d2h = (eng.d2h_bytes - d2h0) / args.steps
 
     if rank != 0:
         D.barrier()
@@ -399,7 +476,7 @@ def run_own_arm(args):
 
     tflops = G * FLOP_PER_POSITION / fwd_avg / 1e9
     peak_tf = peaks["bf16_tflops_sustained"]
-    step_share = None if args.graphs else fwd_avg * n_fwd / s0.elapsed_time(s1)
+    step_share = None if args.graphs else fwd_avg * n_fwd / s0_s1_ms
     forward = {"kernel": f"bf16 Net.forward over the leaf batch (conv_impl={base_eval.conv_impl}: 3x3 tower on "
                          + ("K9 ccz::conv3x3_c256_kernel" if base_eval.conv_impl.startswith("k9") else "cuDNN")
                          + (", stem on K10 ccz::stem::stem_lookup_kernel from the board records" if not base_eval.needs_planes
@@ -420,7 +497,7 @@ def run_own_arm(args):
                 "launches_per_forward": per_fwd,
                 "ms_plain": sum(k_plain) / len(k_plain) if k_plain else None,
                 "ms_with_skip": sum(k_skip) / len(k_skip) if k_skip else None,
-                "share_of_step": k_avg * per_fwd * n_fwd / s0.elapsed_time(s1),
+                "share_of_step": k_avg * per_fwd * n_fwd / s0_s1_ms,
                 "peak_source": peaks["source"] + " sustained", "forward": forward}
     else:
         roof = {"bound": "tensor", "achieved": tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": tflops / peak_tf,
@@ -433,29 +510,39 @@ def run_own_arm(args):
         "dtype": "bf16", "data": "synthetic (random-init net, torch.manual_seed(0); games from the start position)",
         "config": {
             "workload": workload_name(G, P),
-            "games_per_gpu": G, "n_playout": P, "node_cap": args.node_cap, "cuda_graphs": bool(args.graphs),
-            "resident_samples_kept_on_device": resident_samples, "parallelism": f"games sharded x{world}, "
+            "games_per_gpu": G, "n_playout": P, "cuda_graphs": bool(args.graphs), "max_game_moves": M,
+            "slots": "games are cut after max_game_moves and the slots start staggered: G / max_game_moves games finish (and are "
+                     "replaced from the start position) with every move, the steady state of a long run",
+            "resident_samples_drained_in_timed_region": resident_samples, "parallelism": f"games sharded x{world}, "
             "no collective on the hot path",
             "l2": "per-layer activations 4096x256x90 bf16 = 189 MB > 126 MB L2 (inputs larger than L2)",
             "step": "one lockstep move = n_playout x (select, movegen+encode, bf16 forward, expand+backup) + move "
                     "choice + re-root + terminal test + slot refill",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps,
-                "api": "SelfPlayEngine.play_move(): per-move visit counts / boards / flags read back to pinned host "
-                       "memory, host-side visit softmax + seeded Dirichlet choice, chosen moves uploaded"},
-        "gpu_launches": args.steps * (P * (3 + k9_per_fwd) + 4),
+                "ms_per_step": e2e_ms / args.steps, "games_finished": games_finished, "replay": replay_info,
+                "api": "collect.CollectPipeline.collect_data() (the reference's collect.py entry point): SelfPlayEngine.play_move() "
+                       "-- per-move visit counts / boards / flags read back to pinned host memory, host-side visit softmax + "
+                       "seeded Dirichlet choice, chosen moves uploaded -- then K8 replay packing of the finished games and the "
+                       "reference-layout data.h5 shard written by the writer thread, flushed inside the timed region"},
+        # `value` region: per playout K3 select, K1 movegen, K4/K5 expand+backup, K10 stem, 80 x K9; per move the reserve
+        # guard, K6 root read-out, K7a/K7b advance, K1 flags, reset
+        "gpu_launches": args.steps * (P * (3 + k9_per_fwd) + 6),
+        "pool": {"e2e": pool_e2e, "value": pool_value,
+                 "note": "shared MCTS page pool (csrc/ccz_mcts.cuh): expand_failed / trees_dropped must be 0"},
         "roofline": roof,
+        "e2e_warmup": e2e_warmup,
         "clocks": clocks,
         "evals_per_move": P,
     }
-    if not args.no_movegen:
+    del eng
+    torch.cuda.empty_cache()
+    # configs[1] / configs[4] / the CPU baseline ride along at N = 1 only (the scaling runs time self-play)
+    if not args.no_movegen and world == 1:
         line["movegen"] = bench_movegen(torch, _lib, args.movegen_positions, peaks)
-    if not args.no_train:
-        del eng, ev
-        torch.cuda.empty_cache()
+    if not args.no_train and world == 1:
         line["train"] = bench_train(torch)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_moves, P)
     print(json.dumps(line))
     D.barrier()

@@ -4,9 +4,9 @@ Imports the UNMODIFIED reference modules (tools, mcts, net, game, collect) from 
 after installing stand-ins for the packages it needs but the container lacks:
 ``cchess`` -> oracle.cchess_shim, ``cchess.svg``, ``IPython.display``, ``h5py``, ``frontend``.
 
-/root/reference only exists in the authoring container: tests that use this module skip on the
-GPU box and rely on the golden fixtures under tests/golden/ that scripts/make_golden.py wrote
-from it.
+/root/reference only exists in the authoring container.  Parity tests never depend on it at run
+time (they use the golden fixtures under tests/golden/ that scripts/make_golden.py wrote from it); the
+reference arm of bench.py uses the git-ignored snapshot ``oracle/_ref`` (oracle/make_ref.py) on the GPU box.
 """
 from __future__ import annotations
 
@@ -15,7 +15,20 @@ import os
 import sys
 import types
 
-REFERENCE_DIR = os.environ.get("CCZ_REFERENCE_DIR", "/root/reference")
+_SNAPSHOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # written by oracle/make_ref.py
+
+
+def _find_reference() -> str:
+    """/root/reference in the authoring container; on the GPU box the git-ignored snapshot oracle/_ref."""
+    env = os.environ.get("CCZ_REFERENCE_DIR")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/mcts.py"):
+        return "/root/reference"
+    return _SNAPSHOT
+
+
+REFERENCE_DIR = _find_reference()
 
 
 def available() -> bool:

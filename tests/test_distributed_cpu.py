@@ -64,12 +64,46 @@ def test_reference_arm_only_rank0_works():
     assert p.returncode == 0 and p.stdout.strip() == ""
 
 
-def test_reference_arm_prints_contract_line():
+import pytest
+
+
+@pytest.mark.parametrize("kind", ["reference", "port"])
+def test_reference_arm_prints_contract_line(kind, tmp_path):
+    """--impl reference: the UNMODIFIED reference modules when a copy is reachable (/root/reference here, the
+    oracle/_ref snapshot on the GPU box), else the oracle port; --warmup is honoured either way."""
+    from oracle import load_reference
+
+    if kind == "reference" and not load_reference.available():
+        pytest.skip("no reference copy reachable")
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    if kind == "port":
+        env["CCZ_REFERENCE_DIR"] = str(tmp_path / "nowhere")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0", "--playouts", "6"], env=env, capture_output=True, text=True, timeout=300)
+                        "--warmup", "1", "--playouts", "6"], env=env, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "moves/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
-    assert line["higher_is_better"] is True and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == kind and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["higher_is_better"] is True and line["steps"] == 1 and line["warmup"] == 1
+
+
+def test_reference_snapshot_recipe(tmp_path):
+    """oracle/make_ref.py copies exactly the reference's self-play modules, unmodified, into the git-ignored
+    oracle/_ref; the snapshot alone is enough to drive the reference arm."""
+    from oracle import make_ref
+
+    if not os.path.isfile(os.path.join(make_ref.SRC, "mcts.py")):
+        pytest.skip("reference sources not present (GPU box)")
+    out = make_ref.ensure_ref()
+    import filecmp
+
+    assert sorted(os.listdir(out)) == sorted(set(make_ref.MODULES) | ({"__pycache__"} & set(os.listdir(out))))
+    for name in make_ref.MODULES:
+        assert filecmp.cmp(os.path.join(make_ref.SRC, name), os.path.join(out, name), shallow=False)
+    ignored = subprocess.run(["git", "check-ignore", "oracle/_ref/mcts.py"], cwd=ROOT, capture_output=True, text=True)
+    assert ignored.returncode == 0
+    code = ("import sys; sys.path.insert(0, %r); from oracle import reference_arm as r; "
+            "sp = r.ReferenceSelfPlay(n_playout=4, threads=2); print(sp.play_move()[0] >= 0)" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CCZ_REFERENCE_DIR=out, CUDA_VISIBLE_DEVICES=""),
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith("True"), p.stderr[-2000:]
