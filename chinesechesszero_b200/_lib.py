@@ -32,7 +32,8 @@ POLICY_PROBS, POLICY_LOGITS = 0, 1
 CONV_VARIANT_1CTA, CONV_VARIANT_PAIR, CONV_VARIANT_2PAIRS, CONV_VARIANT_4PAIRS = 1, 2, 2 | 32, 2 | 64
 
 EXPORTS = (
-    "ccz_version", "ccz_last_error", "ccz_init", "ccz_action_table", "ccz_boards_start",
+    "ccz_version", "ccz_last_error", "ccz_init", "ccz_action_table", "ccz_set_order_policy", "ccz_get_order_policy",
+    "ccz_boards_start",
     "ccz_movegen_encode", "ccz_board_keys_init", "ccz_board_push", "ccz_mcts_pool_init", "ccz_mcts_reset",
     "ccz_mcts_reserve", "ccz_mcts_migrate", "ccz_mcts_select",
     "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack", "ccz_conv3x3_c256", "ccz_conv3x3_plan", "ccz_stem_lookup",
@@ -102,6 +103,8 @@ def load() -> ctypes.CDLL:
     lib.ccz_init.restype = i32
     lib.ccz_action_table.argtypes = [vp, vp, vp]
     lib.ccz_boards_start.argtypes = [vp, i32, vp]
+    lib.ccz_set_order_policy.argtypes = [vp]
+    lib.ccz_get_order_policy.argtypes = [vp]
     lib.ccz_movegen_encode.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.ccz_board_keys_init.argtypes = [vp, i32, vp, vp]
     lib.ccz_board_push.argtypes = [vp, vp, i32, vp, vp]
@@ -121,6 +124,13 @@ def load() -> ctypes.CDLL:
         if name not in ("ccz_last_error",):
             getattr(lib, name).restype = i32
     _lib = lib
+    # generation order pinned against a real cchess (scripts/pin_cchess.py writes this file next to the library)
+    pinned = os.path.join(os.path.dirname(os.path.abspath(__file__)), "order_policy.json")
+    if os.path.exists(pinned):
+        import json
+
+        with open(pinned) as f:
+            set_order_policy(json.load(f))
     return lib
 
 
@@ -153,6 +163,33 @@ def host_action_table():
     if n != N_ACTIONS:
         raise CczError(f"ccz_action_table returned {n}")
     return id_of.reshape(90, 90), fr, to
+
+
+PIECE_SYMBOLS = (None, "p", "c", "r", "n", "b", "a", "k")  # piece type 1..7 (ccz_rules.cuh)
+DEFAULT_ORDER_POLICY = {"class_rank": {"p": 1, "c": 0, "r": 0, "n": 0, "b": 0, "a": 0, "k": 0},
+                        "from_descending": 1, "to_descending": 1, "capture_mode": 0}
+
+
+def set_order_policy(policy: dict | None = None) -> None:
+    """Generation order of the legal moves K1 emits (``ccz_order_policy``; None = the default).  A dict as
+    ``DEFAULT_ORDER_POLICY`` -- what ``scripts/pin_cchess.py`` stores under "order_policy" in
+    tests/golden/cchess_pin.json.  Library-wide host state: set it before any search starts."""
+    if policy is None:
+        check(load().ccz_set_order_policy(None), "ccz_set_order_policy")
+        return
+    ranks = [0] * 8
+    for sym, r in policy["class_rank"].items():
+        ranks[PIECE_SYMBOLS.index(sym)] = int(r)
+    raw = bytes(ranks + [int(policy["from_descending"]), int(policy["to_descending"]), int(policy["capture_mode"]), 0])
+    check(load().ccz_set_order_policy(ctypes.create_string_buffer(raw, 12)), "ccz_set_order_policy")
+
+
+def get_order_policy() -> dict:
+    buf = ctypes.create_string_buffer(12)
+    check(load().ccz_get_order_policy(buf), "ccz_get_order_policy")
+    b = buf.raw
+    return {"class_rank": {PIECE_SYMBOLS[t]: b[t] for t in range(1, 8)}, "from_descending": b[8],
+            "to_descending": b[9], "capture_mode": b[10]}
 
 
 # ---- tensor-level wrappers ------------------------------------------------------------------

@@ -50,6 +50,11 @@ struct HostTables {
 };
 HostTables g_tab;
 bool g_dev_ready[64] = {false};
+// generation-order policy (see ccz_set_order_policy): host copy, uploaded to every device on its next use
+const ccz_order_policy kDefaultPolicy = {{0, 1, 0, 0, 0, 0, 0, 0}, 1, 1, 0, 0};
+ccz_order_policy g_policy = kDefaultPolicy;
+bool g_policy_is_default = true;
+unsigned g_policy_version = 1, g_dev_policy_version[64] = {0};
 
 int sq_of(const char *s) { return (s[0] - 'a') + 9 * (s[1] - '0'); }
 
@@ -182,6 +187,10 @@ int ensure_device() {
     int dev = 0;
     CCZ_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(-3, "device index out of range");
+    if (g_dev_policy_version[dev] != g_policy_version) {
+        CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_order_policy, &g_policy, sizeof(g_policy)));
+        g_dev_policy_version[dev] = g_policy_version;
+    }
     if (g_dev_ready[dev]) return 0;
     CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_id_of, g_tab.id_of, sizeof(g_tab.id_of)));
     CCZ_CUDA(cudaMemcpyToSymbol(ccz::d_from_of, g_tab.from_of, sizeof(g_tab.from_of)));
@@ -246,6 +255,27 @@ int ccz_action_table(int16_t *id_of, uint8_t *from_of, uint8_t *to_of) {
     return ccz::N_ACTIONS;
 }
 
+int ccz_set_order_policy(const ccz_order_policy *p) {
+    static_assert(sizeof(ccz_order_policy) == 12, "ccz_order_policy layout");
+    const ccz_order_policy &q = p ? *p : kDefaultPolicy;
+    if (q.capture_mode > 2 || q.from_descending > 1 || q.to_descending > 1)
+        return fail(-1, "ccz_set_order_policy: from_descending / to_descending must be 0|1, capture_mode 0|1|2");
+    for (int t = 1; t <= 7; ++t)
+        if (q.class_rank[t] > 7) return fail(-1, "ccz_set_order_policy: class_rank must be 0..7");
+    g_policy = q;
+    g_policy.class_rank[0] = 0;
+    g_policy.reserved = 0;
+    g_policy_is_default = std::memcmp(&g_policy, &kDefaultPolicy, sizeof(g_policy)) == 0;
+    ++g_policy_version; // uploaded (synchronously, cudaMemcpyToSymbol) by the next entry point on each device
+    return 0;
+}
+
+int ccz_get_order_policy(ccz_order_policy *out) {
+    if (!out) return fail(-1, "ccz_get_order_policy: NULL");
+    *out = g_policy;
+    return 0;
+}
+
 int ccz_boards_start(uint8_t *d_boards, int n, ccz_stream_t s) {
     if (n < 0 || (n > 0 && !d_boards)) return fail(-1, "ccz_boards_start: bad arguments");
     if (int rc = ensure_device()) return rc;
@@ -273,13 +303,18 @@ int ccz_movegen_encode(const uint8_t *d_boards, int n, int16_t *d_move_ids, int1
     CCZ_CUDA(cudaGetDevice(&dev));
     if (!claim_base[dev]) {
         // static smem (tables + per-warp scratch) wants the full shared-memory carve-out
-        cudaFuncSetAttribute(ccz::movegen_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(ccz::movegen_encode_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(ccz::movegen_encode_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         CCZ_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&claim_base[dev]), ccz::d_mg_counter));
     }
     unsigned int *claim = claim_base[dev] + (launch_no++ % ccz::MG_COUNTER_SLOTS);
     CCZ_CUDA(cudaMemsetAsync(claim, 0, sizeof(unsigned int), s));
-    ccz::movegen_encode_kernel<<<grid, ccz::MG_WARPS * 32, 0, s>>>(d_boards, n, d_move_ids, d_counts, d_flags,
-                                                                  static_cast<uint32_t *>(d_planes_bf16), claim);
+    if (g_policy_is_default)
+        ccz::movegen_encode_kernel<false><<<grid, ccz::MG_WARPS * 32, 0, s>>>(d_boards, n, d_move_ids, d_counts, d_flags,
+                                                                             static_cast<uint32_t *>(d_planes_bf16), claim);
+    else // a non-default generation order: the same kernel + a warp sort of each legal list (ccz_set_order_policy)
+        ccz::movegen_encode_kernel<true><<<grid, ccz::MG_WARPS * 32, 0, s>>>(d_boards, n, d_move_ids, d_counts, d_flags,
+                                                                            static_cast<uint32_t *>(d_planes_bf16), claim);
     return check_launch("movegen_encode_kernel");
 }
 

@@ -381,10 +381,55 @@ __device__ __forceinline__ void encode_quad(const MgWarpSmem &w, uint32_t *out, 
     }
 }
 
+// ---- generation-order policy (ccz_order_policy in include/ccz_b200.h) ---------------------------------
+// `board.legal_moves` order decides every MCTS tie-break (mcts.py:59-61) and cchess is not available to
+// pin it, so the order is a POLICY: moves are sorted by (class_rank[piece type], from-square key, capture
+// key, to-square key).  The default policy is the order movegen_one generates natively (non-pawns by
+// from-square descending, destinations descending, then pawns) and costs nothing; any other policy runs
+// the SORTED instantiation, which re-orders the legal ids of a position with a warp rank sort.
+__constant__ uint8_t d_order_policy[12] = {0, 1, 0, 0, 0, 0, 0, 0, /*from_desc*/ 1, /*to_desc*/ 1, /*capture_mode*/ 0, 0};
+
+__device__ __forceinline__ uint32_t order_key(const uint8_t *B, int id) {
+    const int f = d_from_of[id], t = d_to_of[id];
+    const uint32_t cls = d_order_policy[B[f] & 7];
+    const uint32_t fk = d_order_policy[8] ? 89 - f : f, tk = d_order_policy[9] ? 89 - t : t;
+    const uint32_t mode = d_order_policy[10];
+    const uint32_t ck = mode == 0 ? 0u : (uint32_t)((B[t] != 0) != (mode == 2));
+    return cls << 16 | fk << 9 | ck << 8 | tk;
+}
+
+// re-order w.row[0 .. n) by the policy key (keys are distinct: (from, to) is); whole warp
+__device__ __forceinline__ void sort_row_by_policy(MgWarpSmem &w, const uint8_t *B, uint32_t *keys /*smem [128]*/, int n,
+                                                   int lane) {
+    uint32_t my_key[4];
+    int my_id[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = lane + 32 * r;
+        my_id[r] = i < n ? w.row[i] : -1;
+        my_key[r] = i < n ? order_key(B, my_id[r]) : 0xffffffffu;
+        if (i < n) keys[i] = my_key[r];
+    }
+    __syncwarp();
+    int rank[4] = {0, 0, 0, 0};
+    for (int j = 0; j < n; ++j) {
+        const uint32_t kj = keys[j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rank[r] += kj < my_key[r];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (lane + 32 * r < n) w.row[rank[r]] = (int16_t)my_id[r];
+    __syncwarp();
+}
+
+template <bool SORTED>
 __global__ void __launch_bounds__(MG_WARPS * 32, CCZ_MG_MIN_BLOCKS)
 movegen_encode_kernel(const uint8_t *__restrict__ boards, int n, int16_t *__restrict__ move_ids,
                       int16_t *__restrict__ counts, uint8_t *__restrict__ flags, uint32_t *__restrict__ planes,
                       unsigned int *__restrict__ claim) {
+    __shared__ uint32_t s_keys[SORTED ? MG_WARPS * MAX_MOVES : 1];
     __shared__ __align__(16) int16_t s_id_of[8100];
     __shared__ __align__(16) uint16_t s_step[STEP_TAB_ENTRIES];
     __shared__ MgWarpSmem s_w[MG_WARPS];
@@ -414,6 +459,7 @@ CCZ_Q_UNROLL
         for (int q = 0; q < nb; ++q) {
             int n_legal, fl;
             movegen_one(w, w.boards[q], s_id_of, s_step, lane, n_legal, fl);
+            if (SORTED) sort_row_by_policy(w, w.boards[q], s_keys + (SORTED ? warp * MAX_MOVES : 0), n_legal, lane);
 #ifdef CCZ_DEBUG_MV
             if (planes != nullptr) {
                 uint16_t *dump = reinterpret_cast<uint16_t *>(planes) + (size_t)(base + q) * PLANE_ELEMS;

@@ -54,7 +54,36 @@ def lib():
         _lib.xq_start.argtypes = [ctypes.c_void_p]
         _lib.xq_perft.argtypes = [ctypes.c_void_p, ctypes.c_int]
         _lib.xq_push.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        _lib.xq_set_order_policy.argtypes = [ctypes.c_void_p]
+        _lib.xq_get_order_policy.argtypes = [ctypes.c_void_p]
     return _lib
+
+
+DEFAULT_ORDER_POLICY = {"class_rank": {"p": 1, "c": 0, "r": 0, "n": 0, "b": 0, "a": 0, "k": 0},
+                        "from_descending": 1, "to_descending": 1, "capture_mode": 0}
+
+
+def order_policy_bytes(policy) -> bytes:
+    """dict (see DEFAULT_ORDER_POLICY) -> the 12-byte xq_order_policy / ccz_order_policy struct."""
+    ranks = [0] * 8
+    for sym, r in policy["class_rank"].items():
+        ranks[PIECE_SYMBOLS.index(sym)] = int(r)
+    return bytes(ranks + [int(policy["from_descending"]), int(policy["to_descending"]), int(policy["capture_mode"]), 0])
+
+
+def set_order_policy(policy=None) -> None:
+    """Generation order of ``legal_moves`` (None = the default, recalled cchess order)."""
+    raw = None if policy is None else ctypes.create_string_buffer(order_policy_bytes(policy), 12)
+    if lib().xq_set_order_policy(raw) != 0:
+        raise ValueError(f"bad order policy {policy!r}")
+
+
+def get_order_policy() -> dict:
+    buf = ctypes.create_string_buffer(12)
+    lib().xq_get_order_policy(buf)
+    b = buf.raw
+    return {"class_rank": {PIECE_SYMBOLS[t]: b[t] for t in range(1, 8)}, "from_descending": b[8],
+            "to_descending": b[9], "capture_mode": b[10]}
 
 
 _FILES = "abcdefghi"
