@@ -141,20 +141,23 @@ class CollectPipeline:
 
 def merge_h5_shards(shard_paths, out_path, gzip_level=4):
     """Fold per-rank ``data.h5`` shards into one file numbered game_0.. in increasing shard index
-    order (rank-interleaved, as ``global_game_index`` assigned them)."""
-    games = []
-    for p in shard_paths:
-        with h5lite.H5Reader(p) as r:
+    order (rank-interleaved, as ``global_game_index`` assigned them).  Every shard is opened once and the
+    stored (deflated) datasets are copied as they are, so merging costs file I/O, not a second compression."""
+    readers = [h5lite.H5Reader(p) for p in shard_paths]
+    try:
+        games = []
+        for ri, r in enumerate(readers):
             for name in r.root_links():
-                games.append((int(name.split("_")[1]), p, name))
-    games.sort()
-    out = h5lite.H5ReplayWriter(out_path, gzip_level=gzip_level)
-    for _, p, name in games:
-        with h5lite.H5Reader(p) as r:
-            d = r.read_group(name)
-        out.add(d["states"], d["mcts_probs"], d["winners"])
-    n = out.iters
-    out.close()
+                games.append((int(name.split("_")[1]), ri, name))
+        games.sort()
+        out = h5lite.H5ReplayWriter(out_path, gzip_level=gzip_level)
+        for _, ri, name in games:
+            out.add_raw(readers[ri].read_group_raw(name))
+        n = out.iters
+        out.close()
+    finally:
+        for r in readers:
+            r.close()
     return n
 
 

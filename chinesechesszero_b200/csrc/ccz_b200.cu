@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include <string>
@@ -381,8 +382,15 @@ int ccz_mcts_select(const ccz_arena *a, float c_puct, uint8_t *d_leaf_boards, in
     if (int rc = check_arena(a)) return rc;
     if (!d_leaf_boards || !d_leaf_nodes) return fail(-1, "ccz_mcts_select: NULL output");
     if (int rc = ensure_device()) return rc;
-    ccz::mcts_select_kernel<<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, c_puct, d_leaf_boards,
-                                                                                   d_leaf_nodes);
+    // CCZ_SELECT_STAGED=1: the child runs go through shared memory (one TMA bulk copy per level) instead of straight
+    // into registers -- a measurement switch, both variants give identical results
+    static const bool staged = [] { const char *e = std::getenv("CCZ_SELECT_STAGED"); return e && e[0] == '1'; }();
+    if (staged)
+        ccz::mcts_select_kernel<true><<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, c_puct, d_leaf_boards,
+                                                                                             d_leaf_nodes);
+    else
+        ccz::mcts_select_kernel<false><<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, c_puct, d_leaf_boards,
+                                                                                              d_leaf_nodes);
     return check_launch("mcts_select_kernel");
 }
 

@@ -117,15 +117,48 @@ __device__ __forceinline__ int32_t *page_list(const ccz_arena &a, int half, int 
     return a.d_page_list + ((size_t)half * a.n_games + g) * a.max_pages;
 }
 
-// K3: Node.select / puct_value + path pushes (mcts.py:41-61,105-111).  Per level one coalesced
-// 16-byte load per lane brings (N, Q, P, first_child) of a child, the scores are reduced by warp
-// shuffles (lowest index wins ties) and the winner's link word (move, n_child) is the only other
-// dependent load; the move is replayed on a shared-memory board with its incremental key.
+// ---- TMA bulk copy + mbarrier (the STAGED variant of K3) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred P1;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// K3: Node.select / puct_value + path pushes (mcts.py:41-61,105-111).  Per level the child run -- one
+// contiguous array of 16-byte records (N, Q, P, first_child), <= 128 of them, inside one pool page --
+// reaches the lanes either
+//   STAGED = false: as one coalesced 16-byte load per lane straight into registers, or
+//   STAGED = true : through shared memory, staged by ONE TMA bulk copy (cp.async.bulk + mbarrier) issued by
+//                   lane 0, after which the lanes read their records from the staging buffer;
+// the scores are reduced by warp shuffles (lowest index wins ties), the winner's link word (move, n_child)
+// is the only other dependent load, and the move is replayed on a shared-memory board with its
+// incremental key.  Both variants are bit-identical; DESIGN.md has the measured difference.
+template <bool STAGED>
 __global__ void __launch_bounds__(MCTS_WARPS * 32)
 mcts_select_kernel(ccz_arena a, float c_puct, uint8_t *leaf_boards, int32_t *leaf_nodes) {
     __shared__ SelWarpSmem s_w[MCTS_WARPS];
+    __shared__ __align__(16) int4 s_kids[STAGED ? MCTS_WARPS : 1][STAGED ? MAX_MOVES : 1];
+    __shared__ __align__(8) uint64_t s_bar[MCTS_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x * MCTS_WARPS + warp;
+    const uint32_t bar = smem_u32(&s_bar[warp]);
+    if (STAGED) {
+        if (lane == 0) mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
     if (g >= a.n_games) return;
     SelWarpSmem &w = s_w[warp];
     const int4 *nodes = node_vec(a);
@@ -149,13 +182,24 @@ mcts_select_kernel(ccz_arena a, float c_puct, uint8_t *leaf_boards, int32_t *lea
     int node = a.d_root[g];
     int4 cur = nodes[node];
     int nc = link_n_child(links[node].y);
+    uint32_t phase = 0;
     while (nc > 0) {
         const int fc = cur.w;
+        const int4 *kids = nodes + fc;
+        if (STAGED) {
+            if (lane == 0) {
+                mbar_expect_tx(bar, (uint32_t)nc * 16u);
+                bulk_g2s(smem_u32(&s_kids[warp][0]), kids, (uint32_t)nc * 16u, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            kids = &s_kids[warp][0];
+        }
         const double sq = sqrt((double)cur.x); // np.sqrt(parent.visits): fp64, correctly rounded
         double best = -CUDART_INF;
         int best_i = 0x7fffffff;
         for (int i = lane; i < nc; i += 32) {
-            const int4 c = nodes[fc + i];
+            const int4 c = kids[i];
             double sc;
             if (c.x == 0) {
                 sc = CUDART_INF;
@@ -174,7 +218,7 @@ mcts_select_kernel(ccz_arena a, float c_puct, uint8_t *leaf_boards, int32_t *lea
         }
         if (best_i == 0x7fffffff) best_i = 0; // all-NaN scores: max() keeps the first item
         node = fc + best_i;
-        cur = nodes[node]; // L1 hit: the line was just read by the owning lane
+        cur = kids[best_i]; // staged: shared memory; direct: an L1 hit, the line was just read by the owning lane
         const int lw = links[node].y;
         nc = link_n_child(lw);
         if (lane == 0) {
@@ -184,7 +228,7 @@ mcts_select_kernel(ccz_arena a, float c_puct, uint8_t *leaf_boards, int32_t *lea
             w.keys[clock] = key;
             w.board[OFF_CLOCK] = (uint8_t)clock;
         }
-        __syncwarp();
+        __syncwarp(); // also: every lane is done with the staging buffer before the next bulk copy lands
         clock = w.board[OFF_CLOCK];
         key = w.keys[clock];
     }

@@ -74,6 +74,15 @@ def _attribute_msg(name: str, value) -> bytes:
     return head + _pad8(nm) + _pad8(dt) + _pad8(ds) + arr.tobytes()
 
 
+class RawDataset:
+    """A dataset as stored: shape, dtype and either the raw bytes (``gzip_level`` None) or the single deflate
+    chunk this module writes (``gzip_level`` = the level recorded in the filter message)."""
+
+    def __init__(self, shape, dtype, data: bytes, gzip_level: int | None):
+        self.shape, self.dtype, self.data, self.gzip_level = tuple(shape), np.dtype(dtype), data, gzip_level
+        self.ndim = len(self.shape)
+
+
 class H5Writer:
     """Create / append ``game_{k}`` groups; ``mode`` "w" truncates, "a" keeps an existing file."""
 
@@ -102,16 +111,24 @@ class H5Writer:
         self.eof = addr + len(data)
         return addr
 
-    def _write_dataset(self, arr: np.ndarray, gzip_level: int | None) -> int:
-        arr = np.ascontiguousarray(arr)
-        raw = arr.tobytes()
+    def _write_dataset(self, arr, gzip_level: int | None) -> int:
+        """``arr``: an array, or a ``RawDataset`` (shape, dtype and the stored bytes of a dataset read with
+        ``H5Reader.raw_dataset``: merging shards copies the deflate streams instead of recompressing them)."""
+        if isinstance(arr, RawDataset):
+            raw = comp = arr.data
+            gzip_level = arr.gzip_level
+        else:
+            arr = np.ascontiguousarray(arr)
+            raw = arr.tobytes()
+            comp = None
         msgs = [_message(0x0001, _dataspace_msg(arr.shape)), _message(0x0003, _dtype_msg(arr.dtype), 1)]
-        if gzip_level is None or arr.size == 0:
+        if gzip_level is None or int(np.prod(arr.shape)) == 0:
             addr = self._append(raw) if raw else UNDEF
             msgs.append(_message(0x0005, bytes([2, 1, 2, 0])))
             msgs.append(_message(0x0008, bytes([3, 1]) + struct.pack("<QQ", addr, len(raw))))
         else:
-            comp = zlib.compress(raw, gzip_level)
+            if comp is None:
+                comp = zlib.compress(raw, gzip_level)
             chunk_addr = self._append(comp)
             rank = arr.ndim
             key_size = 8 + 8 * (rank + 1)
@@ -123,7 +140,7 @@ class H5Writer:
             msgs.append(_message(0x0005, bytes([2, 3, 2, 0])))
             pipeline = struct.pack("<BB6x", 1, 1) + struct.pack("<HHHH", 1, 0, 1, 1) + struct.pack("<I4x", gzip_level)
             msgs.append(_message(0x000B, pipeline))
-            dims = b"".join(struct.pack("<I", int(d)) for d in arr.shape) + struct.pack("<I", arr.dtype.itemsize)
+            dims = b"".join(struct.pack("<I", int(d)) for d in arr.shape) + struct.pack("<I", np.dtype(arr.dtype).itemsize)
             msgs.append(_message(0x0008, bytes([3, 2, rank + 1]) + struct.pack("<Q", btree) + dims))
         return self._append(_object_header(msgs))
 
@@ -299,7 +316,50 @@ class H5Reader:
         return out
 
     def root_links(self):
-        return self.links(self.root_header)
+        if getattr(self, "_root_links", None) is None:   # the file is read-only while this reader is open
+            self._root_links = self.links(self.root_header)
+        return self._root_links
+
+    def raw_dataset(self, header_addr: int) -> RawDataset | None:
+        """The stored form of a contiguous or single-chunk-deflate dataset (what this module writes); None for
+        any other layout (the caller falls back to ``dataset``)."""
+        shape = dt = layout = None
+        level, filters = None, 0
+        for mtype, data in self.messages(header_addr):
+            if mtype == 0x0001:
+                shape = self._parse_dataspace(data)
+            elif mtype == 0x0003:
+                dt = self._parse_dtype(data)
+            elif mtype == 0x0008:
+                layout = data
+            elif mtype == 0x000B:
+                filters = data[1]
+                if data[0] == 1 and data[1] == 1 and struct.unpack_from("<H", data, 8)[0] == 1:
+                    level = struct.unpack_from("<I", data, 16)[0]
+        if layout is None or layout[0] != 3:
+            return None
+        if layout[1] == 1 and filters == 0:
+            addr, size = struct.unpack_from("<QQ", layout, 2)
+            return RawDataset(shape, dt, b"" if addr == UNDEF else bytes(self.buf[addr:addr + size]), None)
+        if layout[1] == 2 and filters == 1 and level is not None:
+            rank1 = layout[2]
+            btree = struct.unpack_from("<Q", layout, 3)[0]
+            cdims = struct.unpack_from(f"<{rank1}I", layout, 11)[:-1]
+            chunks: list = []
+            if btree != UNDEF:
+                self._chunks(btree, rank1, chunks)
+            if tuple(cdims) == tuple(shape) and len(chunks) == 1 and chunks[0][2] == 0:
+                _, size, _, addr = chunks[0]
+                return RawDataset(shape, dt, bytes(self.buf[addr:addr + size]), int(level))
+        return None
+
+    def read_group_raw(self, name: str) -> dict:
+        """{dataset name: RawDataset | ndarray} of a top-level group, without decompressing where possible."""
+        out = {}
+        for k, a in self.links(self.root_links()[name]).items():
+            raw = self.raw_dataset(a)
+            out[k] = raw if raw is not None else self.dataset(a)
+        return out
 
     @staticmethod
     def _parse_dtype(data: bytes) -> np.dtype:
@@ -468,6 +528,20 @@ class H5ReplayWriter:
             due = (self._pending >= max(64, len(self.w.groups) // 16)
                    or self._clock() - self._last_flush >= self.flush_seconds)
         if due:
+            self.flush()
+        return self.iters
+
+    def add_raw(self, datasets: dict, index: int | None = None) -> int:
+        """Append a game whose datasets are already in stored form (``H5Reader.read_group_raw``)."""
+        k = self.iters if index is None else int(index)
+        gz = {n: (d.gzip_level if isinstance(d, RawDataset) else (None if n == "winners" else self.gzip_level))
+              for n, d in datasets.items()}
+        self.w.create_group(f"game_{k}", datasets, gzip=gz)
+        self.iters = max(self.iters, k + 1) if index is not None else self.iters + 1
+        self.w.attrs["iters"] = np.int64(self.iters)
+        self._pending += 1
+        if self._pending >= max(64, len(self.w.groups) // 16) and self.flush_every is None or \
+                (self.flush_every is not None and self._pending >= self.flush_every):
             self.flush()
         return self.iters
 
