@@ -382,9 +382,9 @@ int ccz_mcts_select(const ccz_arena *a, float c_puct, uint8_t *d_leaf_boards, in
     if (int rc = check_arena(a)) return rc;
     if (!d_leaf_boards || !d_leaf_nodes) return fail(-1, "ccz_mcts_select: NULL output");
     if (int rc = ensure_device()) return rc;
-    // CCZ_SELECT_STAGED=1: the child runs go through shared memory (one TMA bulk copy per level) instead of straight
-    // into registers -- a measurement switch, both variants give identical results
-    static const bool staged = [] { const char *e = std::getenv("CCZ_SELECT_STAGED"); return e && e[0] == '1'; }();
+    // default: the child runs are staged in shared memory by one TMA bulk copy per level; CCZ_SELECT_STAGED=0 loads them
+    // straight into registers instead -- a measurement switch, both variants give identical results
+    static const bool staged = [] { const char *e = std::getenv("CCZ_SELECT_STAGED"); return !(e && e[0] == '0'); }();
     if (staged)
         ccz::mcts_select_kernel<true><<<warps_grid(a->n_games), ccz::MCTS_WARPS * 32, 0, s>>>(*a, c_puct, d_leaf_boards,
                                                                                              d_leaf_nodes);

@@ -30,6 +30,7 @@ ap.add_argument("--games", type=int, default=8192, help="concurrent games per GP
 ap.add_argument("--playouts", type=int, default=800)
 ap.add_argument("--moves", type=int, default=4, help="timed lockstep moves")
 ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--warmup-playouts", type=int, default=None, help="playouts of the warm-up moves (default: --playouts)")
 ap.add_argument("--max-game-moves", type=int, default=4, help="games are cut after this many moves; slots start staggered")
 ap.add_argument("--data-dir", default="/tmp/ccz_config4")
 ap.add_argument("--channels", type=int, default=256)
@@ -53,8 +54,11 @@ pipe = CollectPipeline(n_games=args.games, n_playout=args.playouts, data_dir=arg
 pipe.load_model()
 eng = pipe.engine
 eng.move_count[:] = np.arange(args.games) % args.max_game_moves
+if args.warmup_playouts:
+    eng.n_playout = args.warmup_playouts   # first-call costs (module load, cuBLAS handles, TMA descriptors, writer) only
 for _ in range(args.warmup):
     pipe.collect_data()
+eng.n_playout = args.playouts
 pipe.flush()
 torch.cuda.synchronize()
 D.barrier()
@@ -103,6 +107,7 @@ if rank == 0:
         "workload": f"configs[3]: {world} GPU(s) x {args.games} games x {args.playouts} playouts, per-rank data.h5 shards merged "
                     "into the reference layout", "n_gpus": world, "games_per_gpu": args.games, "n_playout": args.playouts,
         "net": f"{args.blocks}x{args.channels}", "moves_timed": args.moves, "warmup": args.warmup,
+        "warmup_playouts": args.warmup_playouts or args.playouts,
         "max_game_moves": args.max_game_moves, "ms_per_move": worst / args.moves,
         "value": world * args.games * args.moves / worst * 1e3, "unit": "moves/s",
         "timing": "host clock around collect_data() x moves + flush (replay compressed, written, indexed), max over ranks",
