@@ -416,6 +416,9 @@ def run_own_arm(args):
         file1 = os.path.getsize(pipe.data_path)
         replay_info = {
             "games_written": w.games - wr0[0], "samples_written": w.samples - wr0[1],
+            "rows_per_move": (w.samples - wr0[1]) / args.steps, "steady_state_rows_per_move": 2 * G,
+            "note": "rows = samples + their mirrored twins; the first max_game_moves moves of a run write shorter games "
+                    "(slots start staggered in mid-game), the steady state is 2 x games_per_gpu rows per move",
             "raw_mb_per_s": (w.raw_bytes - wr0[2]) / 1e6 / (e2e_ms / 1e3), "file_mb": (file1 - file0) / 1e6,
             "writer_busy_frac": (w.busy_seconds - wr0[3]) / (e2e_ms / 1e3),
             "format": "reference data.h5 layout (game_{k}/states f16 gzip, mcts_probs f64 gzip, winners f64, attr iters), per-rank shard",

@@ -259,7 +259,10 @@ class SelfPlayEngine:
             if ev_done.query():
                 ctl, lag = buf.numpy(), age
                 break
+        grown = s.pool_grown
         s.run(self.evaluator, self.n_playout, ctl=ctl, may_sync=False, ctl_lag=lag)
+        if s.pool_grown != grown:
+            r["ctl_snaps"].clear()  # they describe the pool that was just replaced
         acts, visits, counts = s.root_visits()
         valid = r["idx"] < counts.view(g, 1)
         lo_temp = max(0.1, self.temp * 0.5)
