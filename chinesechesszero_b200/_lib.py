@@ -37,6 +37,7 @@ EXPORTS = (
     "ccz_movegen_encode", "ccz_board_keys_init", "ccz_board_push", "ccz_mcts_pool_init", "ccz_mcts_reset",
     "ccz_mcts_reserve", "ccz_mcts_migrate", "ccz_mcts_select",
     "ccz_mcts_expand_backup", "ccz_mcts_root_visits", "ccz_mcts_advance", "ccz_replay_pack", "ccz_conv3x3_c256", "ccz_conv3x3_plan", "ccz_stem_lookup",
+    "ccz_heads_pack",
 )
 
 
@@ -120,6 +121,7 @@ def load() -> ctypes.CDLL:
     lib.ccz_conv3x3_c256.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     lib.ccz_stem_lookup.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.ccz_conv3x3_plan.argtypes = [i32, i32, i32, vp]
+    lib.ccz_heads_pack.argtypes = [vp, i32, vp, i32, i32, vp]
     for name in EXPORTS:
         if name not in ("ccz_last_error",):
             getattr(lib, name).restype = i32
@@ -441,6 +443,18 @@ def stem_lookup(boards: torch.Tensor, table: torch.Tensor, bias_turn: torch.Tens
         check(load().ccz_stem_lookup(_ptr(boards), n, _ptr(table), _ptr(bias_turn), out.data_ptr(), stream_ptr(boards.device)),
               "ccz_stem_lookup")
     return out
+
+
+def heads_pack(h: torch.Tensor, operands: torch.Tensor, value_off: int) -> torch.Tensor:
+    """K11: ``h`` bf16 (n*90, 32) head-convolution outputs (bias added, before the ReLU) -> ``operands`` bf16 (n, K)
+    with relu(policy) channel-major at column 0 and relu(value) at column ``value_off`` (net.py:96-97,103-104)."""
+    n = operands.shape[0]
+    if h.dtype != torch.bfloat16 or operands.dtype != torch.bfloat16 or tuple(h.shape) != (n * 90, 32):
+        raise CczError("heads_pack: h must be bf16 (n*90, 32) and operands bf16 (n, K)")
+    with torch.cuda.device(h.device):
+        check(load().ccz_heads_pack(_ptr(h), n, _ptr(operands), int(operands.shape[1]), int(value_off), stream_ptr(h.device)),
+              "ccz_heads_pack")
+    return operands
 
 
 def conv3x3_plan(n_boards: int, variant: int = 0, resident_clusters: int = 74) -> dict:

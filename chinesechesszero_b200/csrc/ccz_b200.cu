@@ -15,6 +15,7 @@
 #include "ccz_replay.cuh"
 #include "ccz_conv.cuh"
 #include "ccz_stem.cuh"
+#include "ccz_heads.cuh"
 
 #ifndef CCZ_CONV_DEFAULT_PAIRS
 #define CCZ_CONV_DEFAULT_PAIRS 1
@@ -539,6 +540,19 @@ int ccz_stem_lookup(const uint8_t *d_boards, int n, const void *d_table, const f
                                                                          reinterpret_cast<const float4 *>(d_bias_turn),
                                                                          static_cast<uint4 *>(d_y));
     return check_launch("stem_lookup_kernel");
+}
+
+int ccz_heads_pack(const void *d_h, int n, void *d_operands, int row_elems, int value_off, ccz_stream_t s) {
+    namespace hd = ccz::heads;
+    if (n < 0) return fail(-1, "ccz_heads_pack: n < 0");
+    if (n == 0) return 0;
+    if (!d_h || !d_operands) return fail(-1, "ccz_heads_pack: NULL pointer");
+    if (((uintptr_t)d_h & 15) || ((uintptr_t)d_operands & 3)) return fail(-1, "ccz_heads_pack: h must be 16-byte, operands 4-byte aligned");
+    if ((row_elems & 1) || (value_off & 1) || value_off < hd::N_POLICY * hd::HW || row_elems < value_off + hd::N_VALUE * hd::HW)
+        return fail(-1, "ccz_heads_pack: operand row must hold 1530 policy + 630 value elements at even offsets");
+    hd::heads_pack_kernel<<<n, hd::THREADS, 0, s>>>(static_cast<const uint4 *>(d_h), static_cast<uint32_t *>(d_operands), n,
+                                                  row_elems / 2, value_off / 2);
+    return check_launch("heads_pack_kernel");
 }
 
 } // extern "C"

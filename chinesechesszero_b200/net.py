@@ -276,15 +276,19 @@ class BatchedEvaluator:
         if self.device.type == "cuda":
             # 1x1 heads = a GEMM over the (g*90, C) NHWC pixel rows (a view of the channels_last activations)
             rows = x.permute(0, 2, 3, 1).reshape(g * 90, x.shape[1])
-            h = F.relu_(F.linear(rows, *self._heads_gemm)).view(g, 90, 32)
+            h = F.linear(rows, *self._heads_gemm)
             buf = self._head_buf.get(g)  # [policy operand | value operand], pad columns stay zero
             if buf is None:
                 buf = self._head_buf[g] = torch.zeros((g, self._kp + self._kv), dtype=h.dtype, device=h.device)
                 if len(self._head_buf) > 8:
                     self._head_buf.pop(next(iter(self._head_buf)))
-            # NCHW flatten order (channel-major within a board), net.py:97
-            buf[:, :PLAYS * 90].view(g, PLAYS, 90).copy_(h[:, :, :PLAYS].transpose(1, 2))
-            buf[:, self._kp:self._kp + PIECES * 90].view(g, PIECES, 90).copy_(h[:, :, PLAYS:PLAYS + PIECES].transpose(1, 2))
+            if self.dtype == torch.bfloat16:
+                # K11: ReLU + NHWC -> NCHW flatten order (channel-major within a board, net.py:97) in one launch
+                _lib.heads_pack(h, buf, self._kp)
+            else:
+                h = F.relu_(h).view(g, 90, 32)
+                buf[:, :PLAYS * 90].view(g, PLAYS, 90).copy_(h[:, :, :PLAYS].transpose(1, 2))
+                buf[:, self._kp:self._kp + PIECES * 90].view(g, PIECES, 90).copy_(h[:, :, PLAYS:PLAYS + PIECES].transpose(1, 2))
             logits = F.linear(buf[:, :self._kp], self._fc_pad[0])[:, :N_ACTIONS].float() + self.policy_fc[1]
             v = F.relu_(F.linear(buf[:, self._kp:], self._fc_pad[1], self.value_fc1[1])).float()
         else:

@@ -254,6 +254,13 @@ int ccz_conv3x3_plan(int n_boards, int variant, int resident_clusters, int32_t *
 int ccz_stem_lookup(const uint8_t *d_boards, int n, const void *d_table, const float *d_bias_turn, void *d_y,
                     ccz_stream_t s);
 
+/* K11: ReLU + NHWC -> channel-major packing between the fused 1x1 head convolutions and the FC layers of
+ * Net.forward (net.py:94-107).  d_h: bf16 [n*90][32] head-convolution outputs per pixel row (channels 0..16 policy,
+ * 17..23 value, bias added, before the ReLU).  d_operands: bf16 [n][row_elems]; row b receives
+ * relu(policy) as x.view(-1, 17*90) (net.py:97) at element 0 and relu(value) as x.view(-1, 7*90) (net.py:104) at element
+ * value_off; other elements of the row (GEMM K padding) are left untouched. */
+int ccz_heads_pack(const void *d_h, int n, void *d_operands, int row_elems, int value_off, ccz_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif
