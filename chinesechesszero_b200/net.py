@@ -146,6 +146,7 @@ class BatchedEvaluator:
         self.conv_impl = conv_impl
         self.fused = conv_impl != "torch"
         self.n_evals = 0
+        self.use_heads_pack = os.environ.get("CCZ_HEADS_PACK", "1") != "0"  # K11; "0" = the torch copies (A/B measurements)
         # measurement hook (bench.py): when a list, every K9 launch of the next forwards is bracketed by CUDA
         # events on the launching stream and the (with_skip, start, end) triples are appended to it
         self.conv_events: list | None = None
@@ -282,7 +283,7 @@ class BatchedEvaluator:
                 buf = self._head_buf[g] = torch.zeros((g, self._kp + self._kv), dtype=h.dtype, device=h.device)
                 if len(self._head_buf) > 8:
                     self._head_buf.pop(next(iter(self._head_buf)))
-            if self.dtype == torch.bfloat16:
+            if self.dtype == torch.bfloat16 and self.use_heads_pack:
                 # K11: ReLU + NHWC -> NCHW flatten order (channel-major within a board, net.py:97) in one launch
                 _lib.heads_pack(h, buf, self._kp)
             else:
