@@ -138,3 +138,28 @@ def test_split_evaluator_routes_each_half_to_its_net():
     assert kind == _lib.POLICY_LOGITS and val.tolist() == [1, 1, 2, 2, 2, 2] and pol.shape == (6, 2086)
     assert s.swapped()(None, boards)[2].tolist() == [2, 2, 1, 1, 1, 1]
     assert SplitEvaluator(a, make(3, True), 3).needs_planes is True
+
+
+def test_pool_geometry_helpers():
+    """Host arithmetic of the page pool (no GPU): the worst-case pages of a search and the policy struct encoding."""
+    import ctypes
+
+    from chinesechesszero_b200 import _lib
+
+    # 2048-node pages hold >= 17 child runs of <= 119 nodes; + the partly used page the search starts in
+    assert _lib.search_pages(400, 11) == -(-400 // 17) + 1 == 25
+    assert _lib.search_pages(800, 11) == 49 and _lib.search_pages(1, 11) == 2
+    assert _lib.search_pages(40, 7) == 41          # 128-node pages: one run per page in the worst case
+    assert _lib.NODE_BYTES == 24 and _lib.MAX_CHILDREN == 119
+    # the order policy round-trips through the library's host state
+    odd = {"class_rank": {"p": 0, "c": 2, "r": 2, "n": 1, "b": 1, "a": 1, "k": 3}, "from_descending": 0,
+           "to_descending": 1, "capture_mode": 2}
+    try:
+        _lib.set_order_policy(odd)
+        assert _lib.get_order_policy() == odd
+        bad = ctypes.create_string_buffer(bytes([0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 3, 0]), 12)  # capture_mode 3
+        assert _lib.load().ccz_set_order_policy(bad) < 0 and b"capture_mode" in _lib.load().ccz_last_error()
+        assert _lib.get_order_policy() == odd      # a rejected policy changes nothing
+    finally:
+        _lib.set_order_policy(None)
+    assert _lib.get_order_policy() == _lib.DEFAULT_ORDER_POLICY
