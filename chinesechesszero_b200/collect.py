@@ -127,6 +127,10 @@ class CollectPipeline:
             self.close()
         return self.iters
 
+    def pool_events(self) -> dict:
+        """Counters of the MCTS page pool (``trees_dropped`` / ``expand_failed`` are 0 unless the pool could not grow)."""
+        return self.engine.pool_events() if self.engine is not None else {}
+
     def close(self):
         if self.writer is not None:
             self.writer.close()

@@ -110,6 +110,13 @@ class LockstepSearch:
             return False
         need = (n_pages << self.page_shift) * _lib.NODE_BYTES + (64 << 20)
         if torch.cuda.mem_get_info(self.device)[0] < need:
+            if not getattr(self, "_warned_no_memory", False):
+                self._warned_no_memory = True
+                import warnings
+
+                warnings.warn(f"MCTS page pool cannot grow to {n_pages} pages ({need >> 20} MiB needed): from here on the "
+                              "device-side guard drops the largest kept sub-trees when the pool runs short "
+                              "(pool_stats()['trees_dropped'] counts them)")
             return False
         new = _lib.Arena(self.n_games, n_pages, self.page_shift, self._game_pages(n_pages), self.device)
         _lib.mcts_migrate(old, new)
