@@ -460,6 +460,35 @@ def run_own_arm(args):
     value = world * G * args.steps / dev_ms * 1e3
     resident_samples = sum(int(d["boards"].shape[0]) for d in eng.resident_backlog) * G
     pool_value = eng.pool_events()
+    # K3 on the trees the run ends with (read-only: select writes only the leaf scratch buffers), for `roofline.mcts`
+    mcts_roof = None
+    try:
+        sr = eng.search
+        for _ in range(5):
+            _lib.mcts_select(sr.arena, sr.c_puct, sr.leaf_boards, sr.leaf_nodes)
+        k3 = []
+        for _ in range(20):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            _lib.mcts_select(sr.arena, sr.c_puct, sr.leaf_boards, sr.leaf_nodes)
+            a1.record()
+            k3.append((a0, a1))
+        torch.cuda.synchronize()
+        k3_ms = sum(a.elapsed_time(b) for a, b in k3) / len(k3)
+        k3_traffic = ncu_traffic("mcts_select_kernel", G)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            k3_ncu = json.load(f).get("mcts_select_kernel", {})
+        mcts_roof = {
+            "kernel": "ccz::mcts_select_kernel<1> (K3: child runs staged in shared memory by TMA bulk copies, fp64 PUCT, warp-shuffle argmax)",
+            "bound": "latency (two dependent loads per tree level over 4096 warps); HBM is the nominal roofline",
+            "ms_per_launch": k3_ms, "launches_timed": len(k3), "mean_live_nodes_per_game": float(sr.arena.n_nodes.float().mean()),
+            "traffic": k3_traffic, "achieved": None if k3_traffic is None else k3_traffic / k3_ms / 1e6, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": None if k3_traffic is None else k3_traffic / k3_ms / 1e6 / peaks["hbm_gbs"],
+            "issue_active_pct_ncu": k3_ncu.get("issue_active_pct"), "warps_active_pct_ncu": k3_ncu.get("warps_active_pct"),
+            "note": "traffic and issue utilisation from the committed ncu capture (trees of ~23k nodes), duration live on this run's trees",
+        }
+    except Exception as e:  # noqa: BLE001 - an auxiliary figure must never cost the bench line
+        mcts_roof = {"error": repr(e)}
     if args.graphs:
         # events cannot sit inside a captured graph: attribute the whole step to the forward, which
         # gives a lower bound on its throughput (its live share is 0.99 in the eager run)
@@ -506,6 +535,7 @@ def run_own_arm(args):
         roof = {"bound": "tensor", "achieved": tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": tflops / peak_tf,
                 "traffic": None, "peak_source": peaks["source"] + " sustained", **{k: v for k, v in forward.items()
                                                                                    if k not in ("achieved", "unit", "frac")}}
+    roof["mcts"] = mcts_roof
     k9_per_fwd = {"k9": 80, "k9_skip": 40}.get(base_eval.conv_impl, 0) + (0 if base_eval.needs_planes else 1)  # + K10
     line = {
         "metric": metric_name(P), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
