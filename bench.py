@@ -460,32 +460,34 @@ def run_own_arm(args):
     value = world * G * args.steps / dev_ms * 1e3
     resident_samples = sum(int(d["boards"].shape[0]) for d in eng.resident_backlog) * G
     pool_value = eng.pool_events()
-    # K3 on the trees the run ends with (read-only: select writes only the leaf scratch buffers), for `roofline.mcts`
+    # K3 for `roofline.mcts`: 64 more playouts so that the trees are a few levels deep, then 50 launches in one event
+    # bracket (select only reads the trees and writes the leaf scratch buffers)
     mcts_roof = None
     try:
         sr = eng.search
+        sr.run(ev, 64, may_sync=False)
         for _ in range(5):
             _lib.mcts_select(sr.arena, sr.c_puct, sr.leaf_boards, sr.leaf_nodes)
-        k3 = []
-        for _ in range(20):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(50):
             _lib.mcts_select(sr.arena, sr.c_puct, sr.leaf_boards, sr.leaf_nodes)
-            a1.record()
-            k3.append((a0, a1))
+        a1.record()
         torch.cuda.synchronize()
-        k3_ms = sum(a.elapsed_time(b) for a, b in k3) / len(k3)
-        k3_traffic = ncu_traffic("mcts_select_kernel", G)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             k3_ncu = json.load(f).get("mcts_select_kernel", {})
+        k3_bytes = (k3_ncu.get("dram_bytes_read", 0) + k3_ncu.get("dram_bytes_write", 0)) * G / k3_ncu.get("positions_per_launch", G)
+        k3_gbs = k3_bytes / (k3_ncu["duration_us"] * 1e-6) / 1e9 if k3_ncu.get("duration_us") else None
         mcts_roof = {
             "kernel": "ccz::mcts_select_kernel<1> (K3: child runs staged in shared memory by TMA bulk copies, fp64 PUCT, warp-shuffle argmax)",
             "bound": "latency (two dependent loads per tree level over 4096 warps); HBM is the nominal roofline",
-            "ms_per_launch": k3_ms, "launches_timed": len(k3), "mean_live_nodes_per_game": float(sr.arena.n_nodes.float().mean()),
-            "traffic": k3_traffic, "achieved": None if k3_traffic is None else k3_traffic / k3_ms / 1e6, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": None if k3_traffic is None else k3_traffic / k3_ms / 1e6 / peaks["hbm_gbs"],
-            "issue_active_pct_ncu": k3_ncu.get("issue_active_pct"), "warps_active_pct_ncu": k3_ncu.get("warps_active_pct"),
-            "note": "traffic and issue utilisation from the committed ncu capture (trees of ~23k nodes), duration live on this run's trees",
+            "ms_per_launch_live": a0.elapsed_time(a1) / 50, "launches_timed": 50,
+            "mean_live_nodes_per_game_live": float(sr.arena.n_nodes.float().mean()),
+            "traffic": k3_bytes or None, "achieved": k3_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": None if k3_gbs is None else k3_gbs / peaks["hbm_gbs"], "ms_per_launch_ncu": k3_ncu.get("duration_us", 0) / 1e3,
+            "issue_active_pct": k3_ncu.get("issue_active_pct"), "warps_active_pct": k3_ncu.get("warps_active_pct"),
+            "note": "traffic, achieved GB/s and issue utilisation are those of the committed ncu capture (one launch on trees of "
+                    "~23k nodes per game, profiles/r02_mcts_select_expand_ncu.csv); the live duration is on this run's shallower trees",
         }
     except Exception as e:  # noqa: BLE001 - an auxiliary figure must never cost the bench line
         mcts_roof = {"error": repr(e)}
