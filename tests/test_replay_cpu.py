@@ -181,3 +181,32 @@ def test_shard_numbering_survives_a_restart(tmp_path):
     for rank in range(world):
         with h5lite.H5Reader(str(tmp_path / f"rank{rank}" / "data.h5")) as r:
             assert sorted(int(n.split("_")[1]) for n in r.root_links()) == [rank + world * i for i in range(6)]
+
+
+def test_writers_keep_host_memory_flat(tmp_path):
+    """the round-1 npy writer held every game in RAM until flush (70 GB at configs[2] sizes).  Both
+    writers stream: after 3,000 games the Python heap has grown by the h5 link table only (a few hundred KB), not
+    by the 100+ MB of rows that went to disk."""
+    import tracemalloc
+
+    rng = np.random.default_rng(7)
+    g = _game(rng, 1)                       # 2 rows = 76 KB raw per game
+    h5 = h5lite.H5ReplayWriter(str(tmp_path / "data.h5"), gzip_level=1)
+    npy = replay.NpyReplayWriter(str(tmp_path))
+    for _ in range(200):                    # warm the allocator
+        h5.add(*g)
+        npy.add(*g)
+    tracemalloc.start()
+    base = tracemalloc.get_traced_memory()[0]
+    for _ in range(3000):
+        h5.add(*g)
+        npy.add(*g)
+    grown = tracemalloc.get_traced_memory()[0] - base
+    peak = tracemalloc.get_traced_memory()[1] - base
+    tracemalloc.stop()
+    written = 3000 * sum(a.nbytes for a in (g[0], g[1], g[2].astype(np.float32)))
+    assert written > 200e6
+    assert grown < 2e6 and peak < 8e6, (grown, peak)
+    h5.close()
+    npy.close()
+    assert np.load(str(tmp_path / "winners.npy"), mmap_mode="r").shape == (6400,)
