@@ -169,7 +169,7 @@ def host_action_table():
 
 PIECE_SYMBOLS = (None, "p", "c", "r", "n", "b", "a", "k")  # piece type 1..7 (ccz_rules.cuh)
 DEFAULT_ORDER_POLICY = {"class_rank": {"p": 1, "c": 0, "r": 0, "n": 0, "b": 0, "a": 0, "k": 0},
-                        "from_descending": 1, "to_descending": 1, "capture_mode": 0}
+                        "from_descending": 1, "to_descending": 1, "capture_mode": 0, "check_king_first": 0}
 
 
 def set_order_policy(policy: dict | None = None) -> None:
@@ -182,7 +182,8 @@ def set_order_policy(policy: dict | None = None) -> None:
     ranks = [0] * 8
     for sym, r in policy["class_rank"].items():
         ranks[PIECE_SYMBOLS.index(sym)] = int(r)
-    raw = bytes(ranks + [int(policy["from_descending"]), int(policy["to_descending"]), int(policy["capture_mode"]), 0])
+    raw = bytes(ranks + [int(policy["from_descending"]), int(policy["to_descending"]), int(policy["capture_mode"]),
+                        int(policy.get("check_king_first", 0))])
     check(load().ccz_set_order_policy(ctypes.create_string_buffer(raw, 12)), "ccz_set_order_policy")
 
 
@@ -191,7 +192,7 @@ def get_order_policy() -> dict:
     check(load().ccz_get_order_policy(buf), "ccz_get_order_policy")
     b = buf.raw
     return {"class_rank": {PIECE_SYMBOLS[t]: b[t] for t in range(1, 8)}, "from_descending": b[8],
-            "to_descending": b[9], "capture_mode": b[10]}
+            "to_descending": b[9], "capture_mode": b[10], "check_king_first": b[11]}
 
 
 # ---- tensor-level wrappers ------------------------------------------------------------------

@@ -260,13 +260,12 @@ int ccz_action_table(int16_t *id_of, uint8_t *from_of, uint8_t *to_of) {
 int ccz_set_order_policy(const ccz_order_policy *p) {
     static_assert(sizeof(ccz_order_policy) == 12, "ccz_order_policy layout");
     const ccz_order_policy &q = p ? *p : kDefaultPolicy;
-    if (q.capture_mode > 2 || q.from_descending > 1 || q.to_descending > 1)
-        return fail(-1, "ccz_set_order_policy: from_descending / to_descending must be 0|1, capture_mode 0|1|2");
+    if (q.capture_mode > 2 || q.from_descending > 1 || q.to_descending > 1 || q.check_king_first > 1)
+        return fail(-1, "ccz_set_order_policy: from_descending / to_descending / check_king_first must be 0|1, capture_mode 0|1|2");
     for (int t = 1; t <= 7; ++t)
         if (q.class_rank[t] > 7) return fail(-1, "ccz_set_order_policy: class_rank must be 0..7");
     g_policy = q;
     g_policy.class_rank[0] = 0;
-    g_policy.reserved = 0;
     g_policy_is_default = std::memcmp(&g_policy, &kDefaultPolicy, sizeof(g_policy)) == 0;
     ++g_policy_version; // uploaded (synchronously, cudaMemcpyToSymbol) by the next entry point on each device
     return 0;

@@ -387,11 +387,13 @@ __device__ __forceinline__ void encode_quad(const MgWarpSmem &w, uint32_t *out, 
 // key, to-square key).  The default policy is the order movegen_one generates natively (non-pawns by
 // from-square descending, destinations descending, then pawns) and costs nothing; any other policy runs
 // the SORTED instantiation, which re-orders the legal ids of a position with a warp rank sort.
-__constant__ uint8_t d_order_policy[12] = {0, 1, 0, 0, 0, 0, 0, 0, /*from_desc*/ 1, /*to_desc*/ 1, /*capture_mode*/ 0, 0};
+__constant__ uint8_t d_order_policy[12] = {0, 1, 0, 0, 0, 0, 0, 0, /*from_desc*/ 1, /*to_desc*/ 1, /*capture_mode*/ 0,
+                                           /*check_king_first*/ 0};
 
-__device__ __forceinline__ uint32_t order_key(const uint8_t *B, int id) {
+__device__ __forceinline__ uint32_t order_key(const uint8_t *B, int id, bool in_check) {
     const int f = d_from_of[id], t = d_to_of[id];
-    const uint32_t cls = d_order_policy[B[f] & 7];
+    uint32_t cls = d_order_policy[B[f] & 7];
+    if (d_order_policy[11] && in_check) cls = (B[f] & 7) == KING ? 0u : cls + 1u; // evasions: king moves first
     const uint32_t fk = d_order_policy[8] ? 89 - f : f, tk = d_order_policy[9] ? 89 - t : t;
     const uint32_t mode = d_order_policy[10];
     const uint32_t ck = mode == 0 ? 0u : (uint32_t)((B[t] != 0) != (mode == 2));
@@ -400,14 +402,14 @@ __device__ __forceinline__ uint32_t order_key(const uint8_t *B, int id) {
 
 // re-order w.row[0 .. n) by the policy key (keys are distinct: (from, to) is); whole warp
 __device__ __forceinline__ void sort_row_by_policy(MgWarpSmem &w, const uint8_t *B, uint32_t *keys /*smem [128]*/, int n,
-                                                   int lane) {
+                                                   bool in_check, int lane) {
     uint32_t my_key[4];
     int my_id[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int i = lane + 32 * r;
         my_id[r] = i < n ? w.row[i] : -1;
-        my_key[r] = i < n ? order_key(B, my_id[r]) : 0xffffffffu;
+        my_key[r] = i < n ? order_key(B, my_id[r], in_check) : 0xffffffffu;
         if (i < n) keys[i] = my_key[r];
     }
     __syncwarp();
@@ -459,7 +461,8 @@ CCZ_Q_UNROLL
         for (int q = 0; q < nb; ++q) {
             int n_legal, fl;
             movegen_one(w, w.boards[q], s_id_of, s_step, lane, n_legal, fl);
-            if (SORTED) sort_row_by_policy(w, w.boards[q], s_keys + (SORTED ? warp * MAX_MOVES : 0), n_legal, lane);
+            if (SORTED)
+                sort_row_by_policy(w, w.boards[q], s_keys + (SORTED ? warp * MAX_MOVES : 0), n_legal, (fl & CCZ_FLAG_CHECK) != 0, lane);
 #ifdef CCZ_DEBUG_MV
             if (planes != nullptr) {
                 uint16_t *dump = reinterpret_cast<uint16_t *>(planes) + (size_t)(base + q) * PLANE_ELEMS;

@@ -131,7 +131,8 @@ int ccz_action_table(int16_t *id_of, uint8_t *from_of, uint8_t *to_of);
 /* Generation order of `board.legal_moves` (net.py:154-157), which is the insertion order of the tree's
  * children and so decides every PUCT tie-break (mcts.py:59-61).  cchess is not pinned by the reference and
  * not installable where this library is built, so the order is a policy: legal moves come out sorted by
- * (class_rank[piece type], from-square, capture flag, to-square).  The default -- non-pawn pieces by
+ * (class_rank[piece type] -- the king ahead of everything while in check if check_king_first --, from-square,
+ * capture flag, to-square).  The default -- non-pawn pieces by
  * from-square descending, destinations descending, then the pawns likewise (python-chess lineage) -- is the
  * order the kernel generates natively; any other policy adds a warp sort per position.  The oracle mirrors
  * the same struct (xq_set_order_policy); scripts/pin_cchess.py derives the policy from a real cchess. */
@@ -140,7 +141,8 @@ typedef struct {
     uint8_t from_descending; /* 1: larger from-square first */
     uint8_t to_descending;   /* 1: larger to-square first */
     uint8_t capture_mode;    /* 0: destination order only; 1: a piece's quiet moves before its captures; 2: captures first */
-    uint8_t reserved;
+    uint8_t check_king_first; /* 1: when the side to move is in check its king moves come first, then the other pieces by
+                                 class (python-chess generates evasions that way); 0: same order in and out of check */
 } ccz_order_policy;
 
 /* NULL = the default policy.  Host-side state of the library: takes effect for every later call on any device

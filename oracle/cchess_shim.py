@@ -60,7 +60,7 @@ def lib():
 
 
 DEFAULT_ORDER_POLICY = {"class_rank": {"p": 1, "c": 0, "r": 0, "n": 0, "b": 0, "a": 0, "k": 0},
-                        "from_descending": 1, "to_descending": 1, "capture_mode": 0}
+                        "from_descending": 1, "to_descending": 1, "capture_mode": 0, "check_king_first": 0}
 
 
 def order_policy_bytes(policy) -> bytes:
@@ -68,7 +68,8 @@ def order_policy_bytes(policy) -> bytes:
     ranks = [0] * 8
     for sym, r in policy["class_rank"].items():
         ranks[PIECE_SYMBOLS.index(sym)] = int(r)
-    return bytes(ranks + [int(policy["from_descending"]), int(policy["to_descending"]), int(policy["capture_mode"]), 0])
+    return bytes(ranks + [int(policy["from_descending"]), int(policy["to_descending"]), int(policy["capture_mode"]),
+                        int(policy.get("check_king_first", 0))])
 
 
 def set_order_policy(policy=None) -> None:
@@ -83,7 +84,7 @@ def get_order_policy() -> dict:
     lib().xq_get_order_policy(buf)
     b = buf.raw
     return {"class_rank": {PIECE_SYMBOLS[t]: b[t] for t in range(1, 8)}, "from_descending": b[8],
-            "to_descending": b[9], "capture_mode": b[10]}
+            "to_descending": b[9], "capture_mode": b[10], "check_king_first": b[11]}
 
 
 _FILES = "abcdefghi"

@@ -235,7 +235,7 @@ int xq_in_check(const xq_board *b) {
  * DESCENDING, then the pawns likewise.  scripts/pin_cchess.py derives the policy from a real cchess. */
 typedef struct {
     uint8_t class_rank[8]; /* index = piece type 1..7 */
-    uint8_t from_descending, to_descending, capture_mode, reserved;
+    uint8_t from_descending, to_descending, capture_mode, check_king_first;
 } xq_order_policy;
 static const xq_order_policy XQ_DEFAULT_POLICY = {{0, 1, 0, 0, 0, 0, 0, 0}, 1, 1, 0, 0};
 static xq_order_policy g_policy = {{0, 1, 0, 0, 0, 0, 0, 0}, 1, 1, 0, 0};
@@ -243,16 +243,16 @@ static xq_order_policy g_policy = {{0, 1, 0, 0, 0, 0, 0, 0}, 1, 1, 0, 0};
 int xq_set_order_policy(const uint8_t *p /* 12 bytes or NULL = default */) {
     xq_order_policy q = XQ_DEFAULT_POLICY;
     if (p) memcpy(&q, p, sizeof(q));
-    if (q.capture_mode > 2 || q.from_descending > 1 || q.to_descending > 1) return -1;
+    if (q.capture_mode > 2 || q.from_descending > 1 || q.to_descending > 1 || q.check_king_first > 1) return -1;
     q.class_rank[0] = 0;
-    q.reserved = 0;
     g_policy = q;
     return 0;
 }
 void xq_get_order_policy(uint8_t *out /* 12 bytes */) { memcpy(out, &g_policy, sizeof(g_policy)); }
 
-static uint32_t order_key(const uint8_t *sq, int from, int to) {
-    const uint32_t cls = g_policy.class_rank[type_of(sq[from])];
+static uint32_t order_key(const uint8_t *sq, int from, int to, int in_check) {
+    uint32_t cls = g_policy.class_rank[type_of(sq[from])];
+    if (g_policy.check_king_first && in_check) cls = type_of(sq[from]) == XQ_KING ? 0u : cls + 1u; /* evasions: king first */
     const uint32_t fk = g_policy.from_descending ? 89 - from : from, tk = g_policy.to_descending ? 89 - to : to;
     const uint32_t ck = g_policy.capture_mode == 0 ? 0u : (uint32_t)((sq[to] != 0) != (g_policy.capture_mode == 2));
     return cls << 16 | fk << 9 | ck << 8 | tk;
@@ -265,7 +265,8 @@ int xq_legal_moves(const xq_board *b, uint16_t *moves) {
     const int n = xq_legal_moves_native(b, moves);
     if (memcmp(&g_policy, &XQ_DEFAULT_POLICY, sizeof(g_policy)) != 0) {
         uint32_t keys[128];
-        for (int i = 0; i < n; ++i) keys[i] = order_key(b->sq, moves[i] >> 8, moves[i] & 255);
+        const int in_check = xq_in_check(b);
+        for (int i = 0; i < n; ++i) keys[i] = order_key(b->sq, moves[i] >> 8, moves[i] & 255, in_check);
         for (int i = 1; i < n; ++i) { /* insertion sort: n <= 119, keys distinct */
             const uint32_t k = keys[i];
             const uint16_t m = moves[i];

@@ -124,6 +124,8 @@ def infer_policy(entries) -> tuple[dict | None, dict]:
     before = np.ones((8, 8), dtype=bool)
     seen = np.zeros((8, 8), dtype=bool)
     for e in entries:
+        if e.get("is_check"):
+            continue  # evasions may be generated king-first (check_king_first): classes are read off quiet positions
         sq = e["squares"]
         types = [sq[cs.Move.from_uci(u).from_square] & 7 for u in e["legal"]]
         first, last = {}, {}
@@ -145,8 +147,8 @@ def infer_policy(entries) -> tuple[dict | None, dict]:
     boards = [(shim_board(e).record(), e["legal"]) for e in entries if e["legal"]]
     try:
         for cr in candidates:
-            for fd, td, cm in itertools.product((1, 0), (1, 0), (0, 1, 2)):
-                pol = {"class_rank": cr, "from_descending": fd, "to_descending": td, "capture_mode": cm}
+            for fd, td, cm, kf in itertools.product((1, 0), (1, 0), (0, 1, 2), (0, 1)):
+                pol = {"class_rank": cr, "from_descending": fd, "to_descending": td, "capture_mode": cm, "check_king_first": kf}
                 cs.set_order_policy(pol)
                 report["tried"] += 1
                 if all([m.uci() for m in cs.Board.from_record(rec).legal_moves] == legal for rec, legal in boards):

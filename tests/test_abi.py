@@ -153,7 +153,7 @@ def test_pool_geometry_helpers():
     assert _lib.NODE_BYTES == 24 and _lib.MAX_CHILDREN == 119
     # the order policy round-trips through the library's host state
     odd = {"class_rank": {"p": 0, "c": 2, "r": 2, "n": 1, "b": 1, "a": 1, "k": 3}, "from_descending": 0,
-           "to_descending": 1, "capture_mode": 2}
+           "to_descending": 1, "capture_mode": 2, "check_king_first": 1}
     try:
         _lib.set_order_policy(odd)
         assert _lib.get_order_policy() == odd

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PIN = os.path.join(ROOT, "tests", "golden", "cchess_pin.json")
 
 ODD_POLICY = {"class_rank": {"p": 0, "c": 2, "r": 2, "n": 1, "b": 1, "a": 1, "k": 3},
-              "from_descending": 0, "to_descending": 1, "capture_mode": 2}
+              "from_descending": 0, "to_descending": 1, "capture_mode": 2, "check_king_first": 1}
 
 
 @pytest.fixture
@@ -129,14 +129,20 @@ def test_policy_only_permutes_the_legal_set(default_policy_after):
     base = [[m.uci() for m in cs.Board.from_record(r).legal_moves] for r in recs]
     cs.set_order_policy(ODD_POLICY)
     assert cs.get_order_policy() == ODD_POLICY
+    seen_in_check = [0]
     for r, want in zip(recs, base):
         b = cs.Board.from_record(r)
         got = [m.uci() for m in b.legal_moves]
         assert sorted(got) == sorted(want)
-        # pawns first (class 0), kings last (class 3); within a piece captures come first
+        # pawns first (class 0), kings last (class 3) -- except in check, where the king's moves lead
         types = [int(r[cs.Move.from_uci(u).from_square]) & 7 for u in got]
-        ranks = [{1: 0, 2: 2, 3: 2, 4: 1, 5: 1, 6: 1, 7: 3}[t] for t in types]
+        if b.is_check():
+            seen_in_check[0] += 1
+            ranks = [0 if t == 7 else 1 + {1: 0, 2: 2, 3: 2, 4: 1, 5: 1, 6: 1}[t] for t in types]
+        else:
+            ranks = [{1: 0, 2: 2, 3: 2, 4: 1, 5: 1, 6: 1, 7: 3}[t] for t in types]
         assert ranks == sorted(ranks)
+    assert seen_in_check[0] > 0  # the evasion ordering was exercised
     with pytest.raises(ValueError):
         cs.set_order_policy(dict(ODD_POLICY, capture_mode=3))
 
