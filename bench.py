@@ -412,7 +412,7 @@ def run_own_arm(args):
     d2h = (eng.d2h_bytes + pipe.packer.d2h_bytes - d2h0) / args.steps
     pack_launches = pipe.packer.launches - pack_launch0
     replay_info = None
-    if w is not None:
+    if w is not None and pipe.h5 is not None:
         file1 = os.path.getsize(pipe.data_path)
         replay_info = {
             "games_written": w.games - wr0[0], "samples_written": w.samples - wr0[1],
