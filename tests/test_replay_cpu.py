@@ -210,3 +210,24 @@ def test_writers_keep_host_memory_flat(tmp_path):
     h5.close()
     npy.close()
     assert np.load(str(tmp_path / "winners.npy"), mmap_mode="r").shape == (6400,)
+
+
+def test_packer_chunking_keeps_games_whole():
+    """ReplayPacker._chunks (host logic, no GPU): runs of WHOLE games with at most max_samples samples, order kept,
+    a game longer than max_samples alone in its chunk."""
+    from types import SimpleNamespace
+
+    class Rec:
+        def __init__(self, t):
+            self.t = t
+
+        def __len__(self):
+            return self.t
+
+    lens = [3, 5, 2, 9, 1, 1, 1, 40, 4, 4, 8]
+    recs = [Rec(t) for t in lens]
+    runs = list(replay.ReplayPacker._chunks(SimpleNamespace(max_samples=10), recs))
+    assert [r for run in runs for r in run] == recs                      # nothing lost, order kept
+    assert all(sum(len(r) for r in run) <= 10 or len(run) == 1 for run in runs)
+    assert [[len(r) for r in run] for run in runs] == [[3, 5, 2], [9, 1], [1, 1], [40], [4, 4], [8]]
+    assert list(replay.ReplayPacker._chunks(SimpleNamespace(max_samples=10), [])) == []
